@@ -1,0 +1,546 @@
+// rwmpt_api.cu -- the extern "C" boundary of librwmpt.so (see include/rwmpt.h): argument validation,
+// launch geometry, family dispatch, and the small stand-alone kernels (proposal sampler, PT swap sweep,
+// ESJD reduction, Philox known-answer hook) plus the host-buffer end-to-end entry.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "rwmpt_launch.cuh"
+
+namespace rwmpt {
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(RWMPT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+static const int kFastE[] = {
+#define X(e) e,
+    RWMPT_FAST_E_LIST(X)
+#undef X
+};
+static const int kIeeeE[] = {
+#define X(e) e,
+    RWMPT_IEEE_E_LIST(X)
+#undef X
+};
+
+static int64_t min_params(int family, int d) {
+  const int64_t H = RWMPT_PARAM_HEADER;
+  switch (family) {
+    case RWMPT_T_ROUGH_CARPET: return H;  // + d when P[7] != 0 (checked by the facade; device reads only then)
+    case RWMPT_T_THREE_MIXTURE: return H + 3LL * d;
+    case RWMPT_T_FULL_ROSENBROCK: return H + d - 1;
+    case RWMPT_T_EVEN_ROSENBROCK: return H + d / 2;
+    case RWMPT_T_SCALED_MVN: return H + d;
+    case RWMPT_T_MVN_DIAG: return H + 2LL * d;
+    default: return H;
+  }
+}
+
+static int check_target(const rwmpt_target_t* t) {
+  if (!t) return fail(RWMPT_EINVAL, "target is NULL");
+  if (t->family < 0 || t->family >= RWMPT_T_COUNT) return fail(RWMPT_EINVAL, "unknown target family %d", t->family);
+  if (t->dim < 1) return fail(RWMPT_EINVAL, "dim must be >= 1 (got %d)", t->dim);
+  if (!t->params) return fail(RWMPT_EINVAL, "target params pointer is NULL");
+  if (t->n_params < min_params(t->family, t->dim))
+    return fail(RWMPT_EINVAL, "target family %d with dim %d needs >= %lld params, got %lld", t->family, t->dim,
+                (long long)min_params(t->family, t->dim), (long long)t->n_params);
+  if (t->family == RWMPT_T_EVEN_ROSENBROCK && (t->dim < 2 || t->dim % 2))
+    return fail(RWMPT_EINVAL, "EvenRosenbrock needs an even dim >= 2");
+  if ((t->family == RWMPT_T_FULL_ROSENBROCK) && t->dim < 2) return fail(RWMPT_EINVAL, "FullRosenbrock needs dim >= 2");
+  return RWMPT_OK;
+}
+
+// Choose lanes-per-chain W and elements-per-lane E.  Candidates: E from the compiled list, W a power of two,
+// E*W >= d, no lane entirely padding, and the ladder (K*W threads) must fit one CTA.  Prefer the least padding;
+// among equals prefer more lanes while the grid is too small to fill the machine (latency hiding), else fewer.
+static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_W, LaunchGeom* g) {
+  const int* list = ieee ? kIeeeE : kFastE;
+  const int n_list = ieee ? (int)(sizeof(kIeeeE) / sizeof(int)) : (int)(sizeof(kFastE) / sizeof(int));
+  const long long n_chains = n_ladders * K;
+  const double fill_threads = 148.0 * 4 * 32 * 4;  // ~4 warps per scheduler
+  double best_score = 1e300;
+  int bestE = -1, bestW = -1;
+  for (int W = 1; W <= 32; W *= 2) {
+    if (want_W > 0 && W != want_W) continue;
+    if ((long long)K * W > kMaxCtaThreads) continue;
+    for (int k = 0; k < n_list; ++k) {
+      const int E = list[k];
+      if ((long long)E * W < d) continue;
+      if (W > 1 && (long long)(W - 1) * E >= d) continue;
+      const double waste = (double)E * W / d;
+      const double threads = (double)n_chains * W;
+      double score = waste;
+      if (threads < fill_threads) score *= 1.0 + 0.15 * (fill_threads / threads > 8 ? 3.0 : (fill_threads / threads - 1.0) * 3.0 / 7.0);
+      score += 1e-3 * E;  // mild preference for fewer registers
+      if (score < best_score) { best_score = score; bestE = E; bestW = W; }
+      break;  // list is ascending: first E that fits is the least padded for this W
+    }
+  }
+  if (bestE < 0)
+    return fail(RWMPT_ENOTSUP, "no kernel variant for dim=%d n_temps=%d lanes_per_chain=%d (max dim %d; n_temps*lanes <= %d)",
+                d, K, want_W, list[n_list - 1] * 32, kMaxCtaThreads);
+  g->E = bestE;
+  g->W = bestW;
+  const int ladder_threads = K * bestW;
+  int ladders_per_cta = ladder_threads >= 32 ? 1 : 32 / ladder_threads;
+  g->chains_per_cta = ladders_per_cta * K;
+  g->threads = ((g->chains_per_cta * bestW + 31) / 32) * 32;
+  g->grid = (n_ladders + ladders_per_cta - 1) / ladders_per_cta;
+  g->smem = K > 1 ? (size_t)g->chains_per_cta * (4 + d) * sizeof(float) : 0;
+  return RWMPT_OK;
+}
+
+static int64_t count_rounds(int64_t step_offset, int64_t n_steps, int64_t burn_in, int32_t swap_every) {
+  // sweeps at global steps s in (step_offset, step_offset + n_steps] with s % swap_every == 0 and s > burn_in
+  if (swap_every < 1 || n_steps <= 0) return 0;
+  const int64_t lo = step_offset > burn_in ? step_offset : burn_in;  // s > lo
+  const int64_t hi = step_offset + n_steps;
+  if (hi <= lo) return 0;
+  return hi / swap_every - lo / swap_every;
+}
+
+static cudaError_t dispatch_mcmc(int family, const KernelArgs& a, const LaunchGeom& g, bool ieee, cudaStream_t st) {
+  switch (family) {
+    case RWMPT_T_ROUGH_CARPET: return launch_mcmc_rough_carpet(a, g, ieee, st);
+    case RWMPT_T_THREE_MIXTURE: return launch_mcmc_three_mixture(a, g, ieee, st);
+    case RWMPT_T_FULL_ROSENBROCK: return launch_mcmc_full_rosenbrock(a, g, ieee, st);
+    case RWMPT_T_EVEN_ROSENBROCK: return launch_mcmc_even_rosenbrock(a, g, ieee, st);
+    case RWMPT_T_HYBRID_ROSENBROCK: return launch_mcmc_hybrid_rosenbrock(a, g, ieee, st);
+    case RWMPT_T_NEAL_FUNNEL: return launch_mcmc_neal_funnel(a, g, ieee, st);
+    case RWMPT_T_HYPERCUBE: return launch_mcmc_hypercube(a, g, ieee, st);
+    case RWMPT_T_IID_GAMMA: return launch_mcmc_iid_gamma(a, g, ieee, st);
+    case RWMPT_T_IID_BETA: return launch_mcmc_iid_beta(a, g, ieee, st);
+    case RWMPT_T_SCALED_MVN: return launch_mcmc_scaled_mvn(a, g, ieee, st);
+    case RWMPT_T_MVN_DIAG: return launch_mcmc_mvn_diag(a, g, ieee, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+static cudaError_t dispatch_logp(int family, const float* P, int d, int E, int W, const float* x, long long n, float* out,
+                                 bool ieee, cudaStream_t st) {
+  switch (family) {
+    case RWMPT_T_ROUGH_CARPET: return launch_logp_rough_carpet(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_THREE_MIXTURE: return launch_logp_three_mixture(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_FULL_ROSENBROCK: return launch_logp_full_rosenbrock(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_EVEN_ROSENBROCK: return launch_logp_even_rosenbrock(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_HYBRID_ROSENBROCK: return launch_logp_hybrid_rosenbrock(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_NEAL_FUNNEL: return launch_logp_neal_funnel(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_HYPERCUBE: return launch_logp_hypercube(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_IID_GAMMA: return launch_logp_iid_gamma(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_IID_BETA: return launch_logp_iid_beta(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_SCALED_MVN: return launch_logp_scaled_mvn(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_MVN_DIAG: return launch_logp_mvn_diag(P, d, E, W, x, n, out, ieee, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
+  if (!r) return fail(RWMPT_EINVAL, "args is NULL");
+  int rc = check_target(&r->target);
+  if (rc) return rc;
+  const int d = r->target.dim;
+  if (r->n_temps < 1) return fail(RWMPT_EINVAL, "n_temps must be >= 1");
+  if (require_rwm && r->n_temps != 1) return fail(RWMPT_EINVAL, "rwmpt_rwm_run needs n_temps == 1 (use rwmpt_pt_run)");
+  if (r->n_ladders < 0 || r->n_steps < 0 || r->burn_in < 0 || r->step_offset < 0)
+    return fail(RWMPT_EINVAL, "n_ladders, n_steps, burn_in and step_offset must be >= 0");
+  if (r->proposal_family < RWMPT_P_NORMAL || r->proposal_family > RWMPT_P_UNIFORM_RADIUS)
+    return fail(RWMPT_EINVAL, "unknown proposal family %d", r->proposal_family);
+  if (r->math_mode != RWMPT_MATH_FAST && r->math_mode != RWMPT_MATH_IEEE) return fail(RWMPT_EINVAL, "bad math_mode");
+  if (r->swap_mode != RWMPT_SWAP_REFERENCE && r->swap_mode != RWMPT_SWAP_EXCHANGE) return fail(RWMPT_EINVAL, "bad swap_mode");
+  if (r->n_temps > 1 && r->swap_every < 1) return fail(RWMPT_EINVAL, "swap_every must be >= 1");
+  if (!r->state || !r->logp || !r->beta) return fail(RWMPT_EINVAL, "state, logp and beta must be non-NULL");
+  const bool inject = r->inj_increments != nullptr;
+  if (inject != (r->inj_uniforms != nullptr)) return fail(RWMPT_EINVAL, "inj_increments and inj_uniforms go together");
+  if (!inject && !r->prop_scale) return fail(RWMPT_EINVAL, "prop_scale is required unless increments are injected");
+  if (r->samples) {
+    if (r->store_mode != RWMPT_STORE_COLD && r->store_mode != RWMPT_STORE_ALL)
+      return fail(RWMPT_EINVAL, "samples given but store_mode is NONE");
+    if (r->thin < 1 || r->sample_stride < 1 || r->store_start < 0 || r->sample_rows < 0 || r->sample_rows > r->sample_stride)
+      return fail(RWMPT_EINVAL, "bad thin / sample_stride / sample_rows / store_start");
+  }
+  if (r->lanes_per_chain < 0 || r->lanes_per_chain > 32 || (r->lanes_per_chain & (r->lanes_per_chain - 1)))
+    return fail(RWMPT_EINVAL, "lanes_per_chain must be 0 or a power of two <= 32");
+  if (r->n_ladders == 0 || r->n_steps == 0) return RWMPT_OK;  // empty input: nothing to do
+
+  LaunchGeom g;
+  const bool ieee = r->math_mode == RWMPT_MATH_IEEE;
+  rc = pick_geometry(d, r->n_temps, r->n_ladders, ieee, r->lanes_per_chain, &g);
+  if (rc) return rc;
+  if (g.grid > 2147483647LL) return fail(RWMPT_ENOTSUP, "too many CTAs (%lld)", g.grid);
+
+  KernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.P = r->target.params; a.dim = d; a.prop_family = r->proposal_family; a.K = r->n_temps; a.W = g.W;
+  a.chains_per_cta = g.chains_per_cta;
+  a.swap_every = r->n_temps > 1 ? r->swap_every : 1;
+  a.swap_mode = r->swap_mode; a.store_mode = r->store_mode;
+  a.prop_scale = r->prop_scale; a.prop_dim_scale = r->prop_dim_scale; a.beta = r->beta;
+  a.n_ladders = r->n_ladders; a.n_chains = r->n_ladders * r->n_temps;
+  a.n_steps = r->n_steps; a.burn_in = r->burn_in; a.step_offset = r->step_offset;
+  a.rounds_before = count_rounds(0, r->step_offset, r->burn_in, a.swap_every);
+  a.state = r->state; a.logp = r->logp;
+  a.key0 = (unsigned)(r->seed & 0xffffffffu); a.key1 = (unsigned)(r->seed >> 32);
+  a.chain_id_base = r->chain_id_base;
+  a.samples = r->samples; a.sample_logp = r->sample_logp;
+  a.store_start = r->store_start; a.thin = r->thin < 1 ? 1 : r->thin; a.sample_stride = r->sample_stride; a.sample_rows = r->sample_rows;
+  a.accept_count = r->accept_count; a.sq_jump_sum = r->sq_jump_sum;
+  a.swap_accepts = r->swap_accepts; a.swap_last_attempt = r->swap_last_attempt;
+  a.inj_inc = r->inj_increments; a.inj_u = r->inj_uniforms; a.inj_su = r->inj_swap_uniforms;
+  a.decisions = r->decisions; a.swap_dec = r->swap_decisions;
+
+  cudaError_t e = dispatch_mcmc(r->target.family, a, g, ieee, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "mcmc kernel launch");
+  return RWMPT_OK;
+}
+
+// ---- proposal sampler: one warp per row ---------------------------------------------------------
+__global__ void __launch_bounds__(128) proposal_kernel(int family, int d, float scale, const float* __restrict__ dscale,
+                                                       long long n, unsigned k0, unsigned k1, long long row_base,
+                                                       float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int n_blk = (d + 3) / 4;
+  for (long long r = warp; r < n; r += n_warps) {
+    const unsigned long long rid = (unsigned long long)(row_base + r);
+    float n2 = 0.0f;
+    // pass 1 (UniformRadius only): squared norm of the normal vector; counter-based, so pass 2 regenerates it
+    if (family == RWMPT_P_UNIFORM_RADIUS) {
+      for (int b = lane; b < n_blk; b += 32) {
+        const uint4 w = philox4x32_10((unsigned)b, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
+        float z[4];
+        box_muller<true>(w.x, w.y, z[0], z[1]);
+        box_muller<true>(w.z, w.w, z[2], z[3]);
+        for (int q = 0; q < 4; ++q)
+          if (4 * b + q < d) n2 = fmaf(z[q], z[q], n2);
+      }
+      for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFull, n2, o);
+    }
+    float f = scale;
+    if (family == RWMPT_P_UNIFORM_RADIUS) {
+      const uint4 w = philox4x32_10(0xffffffffu, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
+      const float nrm = sqrtf(n2);
+      const float safe = nrm > 1e-12f ? nrm : 1.0f;
+      f = scale * powf(u01_from_bits(w.x), 1.0f / (float)d) / safe;
+    }
+    for (int b = lane; b < n_blk; b += 32) {
+      const uint4 w = philox4x32_10((unsigned)b, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
+      float v[4];
+      if (family == RWMPT_P_LAPLACE) {
+        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+        for (int q = 0; q < 4; ++q) {
+          const float u = u01_from_bits(ww[q]) - 0.5f;
+          const float arg = fmaxf(-2.0f * fabsf(u), -0.999999f);
+          const float sg = (u > 0.0f) ? 1.0f : ((u < 0.0f) ? -1.0f : 0.0f);
+          const int i = 4 * b + q;
+          const float ds = (dscale && i < d) ? dscale[i] : 1.0f;
+          v[q] = -(scale * ds) * sg * log1pf(arg);
+        }
+      } else {
+        box_muller<true>(w.x, w.y, v[0], v[1]);
+        box_muller<true>(w.z, w.w, v[2], v[3]);
+        for (int q = 0; q < 4; ++q) v[q] *= f;
+      }
+      for (int q = 0; q < 4; ++q)
+        if (4 * b + q < d) out[r * d + 4 * b + q] = v[q];
+    }
+  }
+}
+
+// ---- stand-alone PT swap sweep: one CTA keeps a whole ladder in shared memory --------------------
+__global__ void __launch_bounds__(128) pt_swap_kernel(float* __restrict__ state, float* __restrict__ logp,
+                                                      const float* __restrict__ beta, long long n_ladders, int K, int d,
+                                                      int swap_mode, const float* __restrict__ su, unsigned k0, unsigned k1,
+                                                      long long ladder_base, long long round_index,
+                                                      unsigned char* __restrict__ dec, unsigned long long* __restrict__ acc_out) {
+  extern __shared__ float sm[];
+  float* s_lp = sm;               // [K]
+  float* s_b = sm + K;            // [K]
+  int* s_src = (int*)(sm + 2 * K);  // [K]
+  float* s_x = sm + 3 * K;        // [K, d]
+  KernelArgs ka;  // only the key fields are used by swap_uniform
+  ka.key0 = k0; ka.key1 = k1;
+  for (long long l = blockIdx.x; l < n_ladders; l += gridDim.x) {
+    const long long c0 = l * K;
+    for (int i = threadIdx.x; i < K * d; i += blockDim.x) s_x[i] = state[c0 * d + i];
+    for (int j = threadIdx.x; j < K; j += blockDim.x) { s_lp[j] = logp[c0 + j]; s_b[j] = beta[c0 + j]; s_src[j] = j; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long lg = (unsigned long long)(ladder_base + l);
+      for (int j = 0; j < K - 1; ++j) {
+        const float u = su ? su[l * (K - 1) + j] : swap_uniform(ka, lg, (unsigned long long)round_index, j);
+        bool ok;
+        if (swap_mode == RWMPT_SWAP_REFERENCE) {
+          // slot j+1 still holds its pre-sweep occupant when pair j is examined
+          ok = swap_accept<true>(s_b[j], s_b[j + 1], s_lp[j], s_lp[j + 1], u);
+          if (ok) s_src[j] = j + 1;
+        } else {
+          const int sa = s_src[j], sb = s_src[j + 1];
+          ok = swap_accept<true>(s_b[j], s_b[j + 1], s_lp[sa], s_lp[sb], u);
+          if (ok) { s_src[j] = sb; s_src[j + 1] = sa; }
+        }
+        if (dec) dec[l * (K - 1) + j] = ok ? 1 : 0;
+        if (acc_out && ok) acc_out[l * (K - 1) + j] += 1ull;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * d; i += blockDim.x) {
+      const int j = i / d, q = i - j * d;
+      const int src = s_src[j];
+      if (src != j) state[(c0 + j) * d + q] = s_x[src * d + q];
+    }
+    for (int j = threadIdx.x; j < K; j += blockDim.x)
+      if (s_src[j] != j) logp[c0 + j] = s_lp[s_src[j]];
+    __syncthreads();
+  }
+}
+
+// ---- ESJD reduction over stored samples: warp per row-pair, block partials, one atomic per CTA ---
+__global__ void __launch_bounds__(256) esjd_kernel(const float* __restrict__ samples, long long stride, long long first,
+                                                   long long n, int d, int ctas_per_chain, double* __restrict__ out,
+                                                   unsigned long long* __restrict__ moved) {
+  const long long chain = blockIdx.x / ctas_per_chain;
+  const int part = blockIdx.x % ctas_per_chain;
+  const float* base = samples + (chain * stride + first) * d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  double acc = 0.0;
+  unsigned long long mv = 0;
+  for (long long m = 1 + part * n_warps + warp; m < n; m += (long long)ctas_per_chain * n_warps) {
+    float s = 0.0f;
+    for (int i = lane; i < d; i += 32) {
+      const float df = base[m * d + i] - base[(m - 1) * d + i];
+      s = fmaf(df, df, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    acc += (double)s;
+    mv += s != 0.0f;
+  }
+  __shared__ double s_acc[8];
+  __shared__ unsigned long long s_mv[8];
+  if (lane == 0) { s_acc[warp] = acc; s_mv[warp] = mv; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    unsigned long long tm = 0;
+    for (int w = 0; w < n_warps; ++w) { t += s_acc[w]; tm += s_mv[w]; }
+    atomicAdd(&out[chain], t / (double)(n - 1));
+    if (moved) atomicAdd(&moved[chain], tm);
+  }
+}
+
+__global__ void philox_kat_kernel(const uint32_t* in, uint32_t* out) {
+  const uint4 r = philox4x32_10(in[0], in[1], in[2], in[3], in[4], in[5]);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+}  // namespace rwmpt
+
+using namespace rwmpt;
+
+extern "C" {
+
+int rwmpt_version(void) { return RWMPT_VERSION; }
+const char* rwmpt_last_error(void) { return g_err; }
+uint64_t rwmpt_sizeof_run_args(void) { return sizeof(rwmpt_run_args_t); }
+
+int rwmpt_rwm_run(const rwmpt_run_args_t* args, void* cuda_stream) { return run_impl(args, cuda_stream, true); }
+int rwmpt_pt_run(const rwmpt_run_args_t* args, void* cuda_stream) { return run_impl(args, cuda_stream, false); }
+
+int64_t rwmpt_count_swap_rounds(int64_t step_offset, int64_t n_steps, int64_t burn_in, int32_t swap_every) {
+  return count_rounds(step_offset, n_steps, burn_in, swap_every);
+}
+
+int rwmpt_pick_lanes(int32_t dim, int32_t n_temps, int64_t n_ladders, int32_t math_mode, int32_t* elems_per_lane) {
+  LaunchGeom g;
+  if (dim < 1 || n_temps < 1 || n_ladders < 1) return fail(RWMPT_EINVAL, "dim, n_temps, n_ladders must be >= 1");
+  const int rc = pick_geometry(dim, n_temps, n_ladders, math_mode == RWMPT_MATH_IEEE, 0, &g);
+  if (rc) return rc;
+  if (elems_per_lane) *elems_per_lane = g.E;
+  return g.W;
+}
+
+int rwmpt_log_density(const rwmpt_target_t* target, const float* x, int64_t n, float* out, int32_t math_mode,
+                      void* cuda_stream) {
+  int rc = check_target(target);
+  if (rc) return rc;
+  if (n < 0) return fail(RWMPT_EINVAL, "n must be >= 0");
+  if (n == 0) return RWMPT_OK;
+  if (!x || !out) return fail(RWMPT_EINVAL, "x and out must be non-NULL");
+  LaunchGeom g;
+  const bool ieee = math_mode == RWMPT_MATH_IEEE;
+  rc = pick_geometry(target->dim, 1, n, ieee, 0, &g);
+  if (rc) return rc;
+  cudaError_t e = dispatch_logp(target->family, target->params, target->dim, g.E, g.W, x, n, out, ieee, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "log-density kernel launch");
+  return RWMPT_OK;
+}
+
+int rwmpt_proposal_sample(int32_t proposal_family, int32_t dim, float scale, const float* dim_scale, int64_t n,
+                          uint64_t seed, int64_t row_id_base, float* out, void* cuda_stream) {
+  if (proposal_family < RWMPT_P_NORMAL || proposal_family > RWMPT_P_UNIFORM_RADIUS)
+    return fail(RWMPT_EINVAL, "unknown proposal family %d", proposal_family);
+  if (dim < 1 || n < 0) return fail(RWMPT_EINVAL, "dim must be >= 1 and n >= 0");
+  if (!(scale > 0.0f)) return fail(RWMPT_EINVAL, "scale must be positive");
+  if (n == 0) return RWMPT_OK;
+  if (!out) return fail(RWMPT_EINVAL, "out is NULL");
+  long long blocks = (n + 3) / 4;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  proposal_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)cuda_stream>>>(proposal_family, dim, scale, dim_scale, n,
+                                                                         (unsigned)(seed & 0xffffffffu), (unsigned)(seed >> 32),
+                                                                         row_id_base, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "proposal kernel launch");
+  return RWMPT_OK;
+}
+
+int rwmpt_pt_swap(float* state, float* logp, const float* beta, int64_t n_ladders, int32_t n_temps, int32_t dim,
+                  int32_t swap_mode, const float* swap_uniforms, uint64_t seed, int64_t ladder_id_base,
+                  int64_t round_index, unsigned char* swap_decisions, unsigned long long* swap_accepts,
+                  void* cuda_stream) {
+  if (!state || !logp || !beta) return fail(RWMPT_EINVAL, "state, logp, beta must be non-NULL");
+  if (n_temps < 1 || dim < 1 || n_ladders < 0) return fail(RWMPT_EINVAL, "bad n_temps / dim / n_ladders");
+  if (swap_mode != RWMPT_SWAP_REFERENCE && swap_mode != RWMPT_SWAP_EXCHANGE) return fail(RWMPT_EINVAL, "bad swap_mode");
+  if (n_ladders == 0 || n_temps == 1) return RWMPT_OK;
+  const size_t smem = ((size_t)3 * n_temps + (size_t)n_temps * dim) * sizeof(float);
+  if (smem > 200 * 1024) return fail(RWMPT_ENOTSUP, "ladder of %d x %d floats does not fit in shared memory", n_temps, dim);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(pt_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(pt_swap_kernel)");
+  }
+  long long blocks = n_ladders < 148 * 8 ? n_ladders : 148 * 8;
+  pt_swap_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)cuda_stream>>>(
+      state, logp, beta, n_ladders, n_temps, dim, swap_mode, swap_uniforms, (unsigned)(seed & 0xffffffffu),
+      (unsigned)(seed >> 32), ladder_id_base, round_index, swap_decisions, swap_accepts);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pt_swap kernel launch");
+  return RWMPT_OK;
+}
+
+int rwmpt_esjd_reduce(const float* samples, int64_t n_chains, int64_t stride, int64_t first, int64_t n, int32_t dim,
+                      double* esjd_out, unsigned long long* moved_out, void* cuda_stream) {
+  if (!samples || !esjd_out) return fail(RWMPT_EINVAL, "samples and esjd_out must be non-NULL");
+  if (n_chains < 0 || dim < 1 || first < 0 || n < 0 || first + n > stride) return fail(RWMPT_EINVAL, "bad sizes for esjd_reduce");
+  if (n_chains == 0) return RWMPT_OK;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cudaError_t e = cudaMemsetAsync(esjd_out, 0, sizeof(double) * n_chains, st);
+  if (e != cudaSuccess) return cuda_fail(e, "memset esjd_out");
+  if (moved_out) {
+    e = cudaMemsetAsync(moved_out, 0, sizeof(unsigned long long) * n_chains, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset moved_out");
+  }
+  if (n < 2) return RWMPT_OK;  // fewer than two rows: ESJD is 0 (rwm_gpu_optimized.py:526-527)
+  long long want = (148LL * 8 + n_chains - 1) / n_chains;  // enough CTAs to fill the machine
+  long long maxp = (n - 1 + 7) / 8;
+  int cpc = (int)(want < 1 ? 1 : (want > maxp ? maxp : want));
+  if (cpc < 1) cpc = 1;
+  if (n_chains * cpc > 2147483647LL) return fail(RWMPT_ENOTSUP, "too many chains for esjd_reduce");
+  esjd_kernel<<<(unsigned)(n_chains * cpc), 256, 0, st>>>(samples, stride, first, n, dim, cpc, esjd_out, moved_out);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "esjd kernel launch");
+  return RWMPT_OK;
+}
+
+int rwmpt_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t h[6] = {ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]};
+  uint32_t *d_in = nullptr, *d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_in, sizeof(h));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  e = cudaMalloc(&d_out, 4 * sizeof(uint32_t));
+  if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(e, "cudaMalloc"); }
+  cudaMemcpy(d_in, h, sizeof(h), cudaMemcpyHostToDevice);
+  philox_kat_kernel<<<1, 1>>>(d_in, d_out);
+  e = cudaMemcpy(out, d_out, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(e, "philox KAT");
+  return RWMPT_OK;
+}
+
+// ---- host-buffer end-to-end entry ---------------------------------------------------------------
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void* host = nullptr;
+  bool out = false;
+};
+}  // namespace
+
+int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+  if (!r) return fail(RWMPT_EINVAL, "args is NULL");
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  const int64_t d = r->target.dim, K = r->n_temps;
+  if (d < 1 || K < 1 || r->n_ladders < 0 || r->n_steps < 0) return fail(RWMPT_EINVAL, "bad sizes");
+  const int64_t n_chains = r->n_ladders * K;
+  const int64_t rounds = K > 1 ? count_rounds(r->step_offset, r->n_steps, r->burn_in, r->swap_every) : 0;
+  const int64_t stored_chains = r->store_mode == RWMPT_STORE_ALL ? n_chains : r->n_ladders;
+  rwmpt_run_args_t a = *r;
+  std::vector<DevBuf> bufs;
+  uint64_t h2d = 0, d2h = 0;
+  cudaStream_t st;
+  e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  int rc = RWMPT_OK;
+  auto stage = [&](const void* host, size_t bytes, bool in, bool out) -> void* {
+    if (!host || bytes == 0 || rc) return nullptr;
+    DevBuf b;
+    b.bytes = bytes; b.host = const_cast<void*>(host); b.out = out;
+    cudaError_t ee = cudaMalloc(&b.p, bytes);
+    if (ee != cudaSuccess) { rc = cuda_fail(ee, "cudaMalloc"); return nullptr; }
+    if (in) {
+      ee = cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, st);
+      if (ee != cudaSuccess) rc = cuda_fail(ee, "H2D copy");
+      h2d += bytes;
+    }
+    bufs.push_back(b);
+    return b.p;
+  };
+  a.target.params = (const float*)stage(r->target.params, sizeof(float) * r->target.n_params, true, false);
+  a.prop_scale = (const float*)stage(r->prop_scale, sizeof(float) * n_chains, true, false);
+  a.prop_dim_scale = (const float*)stage(r->prop_dim_scale, sizeof(float) * d, true, false);
+  a.beta = (const float*)stage(r->beta, sizeof(float) * n_chains, true, false);
+  a.state = (float*)stage(r->state, sizeof(float) * n_chains * d, true, true);
+  a.logp = (float*)stage(r->logp, sizeof(float) * n_chains, true, true);
+  a.samples = (float*)stage(r->samples, sizeof(float) * stored_chains * r->sample_stride * d, false, true);
+  a.sample_logp = (float*)stage(r->sample_logp, sizeof(float) * stored_chains * r->sample_stride, false, true);
+  a.accept_count = (unsigned long long*)stage(r->accept_count, 8 * n_chains, true, true);
+  a.sq_jump_sum = (double*)stage(r->sq_jump_sum, 8 * n_chains, true, true);
+  a.swap_accepts = (unsigned long long*)stage(r->swap_accepts, 8 * r->n_ladders * (K > 1 ? K - 1 : 0), true, true);
+  a.swap_last_attempt = (unsigned long long*)stage(r->swap_last_attempt, 8 * n_chains, true, true);
+  a.inj_increments = (const float*)stage(r->inj_increments, sizeof(float) * r->n_steps * n_chains * d, true, false);
+  a.inj_uniforms = (const float*)stage(r->inj_uniforms, sizeof(float) * r->n_steps * n_chains, true, false);
+  a.inj_swap_uniforms = (const float*)stage(r->inj_swap_uniforms, sizeof(float) * rounds * r->n_ladders * (K - 1), true, false);
+  a.decisions = (unsigned char*)stage(r->decisions, (size_t)r->n_steps * n_chains, false, true);
+  a.swap_decisions = (unsigned char*)stage(r->swap_decisions, (size_t)rounds * r->n_ladders * (K > 1 ? K - 1 : 0), false, true);
+  if (!rc) rc = run_impl(&a, st, false);
+  if (!rc) {
+    for (auto& b : bufs) {
+      if (!b.out) continue;
+      e = cudaMemcpyAsync(b.host, b.p, b.bytes, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "D2H copy"); break; }
+      d2h += b.bytes;
+    }
+  }
+  e = cudaStreamSynchronize(st);
+  if (!rc && e != cudaSuccess) rc = cuda_fail(e, "stream synchronize");
+  for (auto& b : bufs) cudaFree(b.p);
+  cudaStreamDestroy(st);
+  if (h2d_bytes) *h2d_bytes = h2d;
+  if (d2h_bytes) *d2h_bytes = d2h;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// rwmpt_common.cuh -- shared device utilities for the sm_100a RWM / PT-RWM kernels:
+// kernel argument block, Philox4x32-10, math policies (fast intrinsics vs IEEE parity), sub-warp reductions.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rwmpt.h"
+
+namespace rwmpt {
+
+constexpr int kMaxCtaThreads = 256;  // a whole ladder (n_temps * lanes_per_chain threads) must fit one CTA
+
+// Device-side argument block (passed by value as the single kernel parameter).
+struct KernelArgs {
+  const float* P;  // target parameters (device)
+  int dim;
+  int prop_family;
+  int K;  // temperatures per ladder
+  int W;  // lanes per chain (power of two <= 32)
+  int chains_per_cta;
+  int swap_every;
+  int swap_mode;
+  int store_mode;
+  const float* prop_scale;
+  const float* prop_dim_scale;
+  const float* beta;
+  long long n_chains;
+  long long n_steps;
+  long long burn_in;
+  long long step_offset;
+  long long rounds_before;  // swap sweeps performed before step_offset (global round numbering)
+  float* state;
+  float* logp;
+  unsigned int key0, key1;
+  long long chain_id_base;
+  float* samples;
+  float* sample_logp;
+  long long store_start, thin, sample_stride, sample_rows;
+  unsigned long long* accept_count;
+  double* sq_jump_sum;
+  unsigned long long* swap_accepts;
+  unsigned long long* swap_last_attempt;
+  const float* inj_inc;
+  const float* inj_u;
+  const float* inj_su;
+  unsigned char* decisions;
+  unsigned char* swap_dec;
+  long long n_ladders;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) -- counter-based, no state in memory.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                                      uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#ifdef __CUDA_ARCH__
+  const uint32_t hi0 = __umulhi(M0, c0), hi1 = __umulhi(M1, c2);
+#else
+  const uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c0) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c2) >> 32);
+#endif
+  const uint32_t lo0 = M0 * c0, lo1 = M1 * c2;
+  const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+  c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                        uint32_t k0, uint32_t k1) {
+  constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += W0;
+    k1 += W1;
+  }
+  uint4 o;
+  o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+
+// torch.rand semantics: 24 random bits -> [0, 1)
+__device__ __forceinline__ float u01_from_bits(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+// (0, 1]: never 0, so log() is finite
+__device__ __forceinline__ float u01_open_low(uint32_t w) { return fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+
+// ------------------------------------------------------------------------------------------------
+// Math policies.  IEEE = parity mode: every operation individually rounded (no FMA contraction),
+// accurate expf/logf, in the reference's operation order.  Fast = MUFU approximations, FMA allowed.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+template <bool IEEE>
+struct Mth;
+
+template <>
+struct Mth<true> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float sq(float a) { return __fmul_rn(a, a); }
+  static __device__ __forceinline__ float exp(float a) { return expf(a); }
+  static __device__ __forceinline__ float log(float a) { return logf(a); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+};
+
+template <>
+struct Mth<false> {
+  static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+  static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+  static __device__ __forceinline__ float div(float a, float b) { return a * rcp_approx(b); }
+  static __device__ __forceinline__ float sq(float a) { return a * a; }
+  static __device__ __forceinline__ float exp(float a) { return ex2_approx(a * kLog2e); }
+  static __device__ __forceinline__ float log(float a) { return lg2_approx(a) * kLn2; }
+  static __device__ __forceinline__ float sqrt(float a) { return sqrt_approx(a); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Sub-warp reductions: the W lanes of a chain are W consecutive lanes of one warp (W power of two).
+// XOR butterflies: every lane of the group ends with the bit-identical result, so all lanes of a chain
+// take the same accept / swap decision without a broadcast.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float group_sum(float v, int W) {
+  if (W > 16) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 16));
+  if (W > 8) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 8));
+  if (W > 4) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 4));
+  if (W > 2) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 2));
+  if (W > 1) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 1));
+  return v;
+}
+
+__device__ __forceinline__ double group_sum_f64(double v, int W) {
+  if (W > 16) v += __shfl_xor_sync(kFull, v, 16);
+  if (W > 8) v += __shfl_xor_sync(kFull, v, 8);
+  if (W > 4) v += __shfl_xor_sync(kFull, v, 4);
+  if (W > 2) v += __shfl_xor_sync(kFull, v, 2);
+  if (W > 1) v += __shfl_xor_sync(kFull, v, 1);
+  return v;
+}
+
+// Per-thread view of where it sits inside its chain.
+struct Ctx {
+  const float* P;  // target params
+  int d;           // dimension
+  int W;           // lanes per chain
+  int sub;         // this lane's index inside the chain group [0, W)
+  int base;        // first global coordinate held by this lane (= sub * E)
+  int lane;        // lane in warp
+  int leader;      // lane (in warp) of sub == 0 of this chain
+};
+
+// value of `v` held by lane `sub+delta` of the same chain (garbage at the group edge: callers mask it)
+__device__ __forceinline__ float from_next_lane(float v) { return __shfl_down_sync(kFull, v, 1); }
+__device__ __forceinline__ float from_prev_lane(float v) { return __shfl_up_sync(kFull, v, 1); }
+__device__ __forceinline__ float from_leader(float v, const Ctx& c) { return __shfl_sync(kFull, v, c.leader); }
+
+}  // namespace rwmpt

@@ -1,0 +1,365 @@
+// rwmpt_kernel.cuh -- the persistent fused multi-step RWM / PT-RWM kernel for sm_100a.
+//
+// One launch runs all n_steps Metropolis steps of every chain.  Chain state, log-density, proposal
+// scale, beta, target parameters and all accumulators live in registers for the whole run; per step a
+// chain draws its increments and its accept-uniform from in-kernel Philox4x32-10, evaluates the target
+// functor on the proposal, reduces over the chain's lanes with XOR shuffles and accepts / rejects.
+// A PT ladder (n_temps chains) is resident in one CTA; every swap_every steps the CTA runs the
+// adjacent-temperature sweep through shared memory.  HBM sees only the initial load, the final store,
+// and (optionally) retained samples / decisions.
+//
+// Thread mapping: a chain's d coordinates are split over W consecutive lanes of a warp, E coordinates per
+// lane held in registers (blocked).  CTA = chains_per_cta chains = whole ladders; small CTAs (usually one
+// warp) so that B chains spread evenly over the 148 SMs.
+//
+// Replaces: _single_step_ultra_fused + ultra_fused_mcmc_step_basic (rwm_gpu_optimized.py:289-336, 9-32),
+// step + ultra_fused_parallel_mcmc_step + _attempt_all_swaps + _add_states_to_chains
+// (pt_rwm_gpu_optimized.py:541-574, 61-84, 594-633, 635-653), and the proposal plugins' samplers.
+#pragma once
+
+#include "rwmpt_common.cuh"
+#include "rwmpt_targets.cuh"
+
+namespace rwmpt {
+
+// ---- normal pair from two Philox words ---------------------------------------------------------
+template <bool IEEE>
+__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1) {
+  const float u1 = u01_open_low(wa);
+  if constexpr (IEEE) {
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif((float)wb * 4.6566128730773926e-10f, &sn, &cs);  // angle = 2*pi*wb/2^32
+    z0 = r * cs;
+    z1 = r * sn;
+  } else {
+    const float r = sqrt_approx(-2.0f * kLn2 * lg2_approx(u1));
+    const float th = (float)wb * 1.4629180792671596e-9f;  // 2*pi/2^32
+    z0 = r * __cosf(th);
+    z1 = r * __sinf(th);
+  }
+}
+
+__host__ __device__ constexpr int philox_calls_per_step(int E) { return (E + 2 + 3) / 4; }
+
+// Raw per-step randomness of one lane: E standard normals or E uniforms, plus the chain's accept uniform
+// and (UniformRadius) radius uniform, both taken from the leader lane.
+template <int E, bool IEEE>
+__device__ __forceinline__ void draw_increments(const KernelArgs& a, const Ctx& c, float (&inc)[E], float& u_acc,
+                                                unsigned long long s, unsigned long long chain_gid, float scale,
+                                                const float (&dscale)[E]) {
+  constexpr int NC = philox_calls_per_step(E);
+  uint32_t w[4 * NC];
+  const uint32_t c0 = (uint32_t)s;
+  const uint32_t c1hi = ((uint32_t)(s >> 32) << 16) | ((uint32_t)c.sub << 8);
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const uint4 r = philox4x32_10(c0, c1hi | (uint32_t)k, (uint32_t)chain_gid, (uint32_t)(chain_gid >> 32), a.key0, a.key1);
+    w[4 * k + 0] = r.x; w[4 * k + 1] = r.y; w[4 * k + 2] = r.z; w[4 * k + 3] = r.w;
+  }
+  u_acc = from_leader(u01_from_bits(w[4 * NC - 1]), c);
+  if (a.prop_family == RWMPT_P_LAPLACE) {
+    // laplace.py:47-69: u in (-.5,.5); -s * sign(u) * log1p(max(-2|u|, -0.999999))
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float u = u01_from_bits(w[e]) - 0.5f;
+      const float arg = fmaxf(-2.0f * fabsf(u), -0.999999f);
+      const float l = IEEE ? log1pf(arg) : lg2_approx(1.0f + arg) * kLn2;
+      const float sg = (u > 0.0f) ? 1.0f : ((u < 0.0f) ? -1.0f : 0.0f);
+      inc[e] = -(scale * dscale[e]) * sg * l;
+    }
+    return;
+  }
+  float z[E + 1];
+#pragma unroll
+  for (int p = 0; p < (E + 1) / 2; ++p) box_muller<IEEE>(w[2 * p], w[2 * p + 1], z[2 * p], z[2 * p + 1]);
+  if (a.prop_family == RWMPT_P_NORMAL) {
+    // normal.py:47-55: randn * std
+#pragma unroll
+    for (int e = 0; e < E; ++e) inc[e] = z[e] * scale;
+  } else {
+    // uniform.py:48-73: z/||z|| * R * u^(1/d)
+    float n2 = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (c.base + e < c.d) n2 = fmaf(z[e], z[e], n2);
+    n2 = group_sum(n2, c.W);
+    const float nrm = IEEE ? sqrtf(n2) : sqrt_approx(n2);
+    const float safe = nrm > 1e-12f ? nrm : 1.0f;
+    const float ur = from_leader(u01_from_bits(w[4 * NC - 2]), c);
+    const float inv_d = 1.0f / (float)c.d;
+    const float rad = IEEE ? scale * powf(ur, inv_d) : scale * ex2_approx(lg2_approx(ur) * inv_d);
+    const float f = IEEE ? rad / safe : rad * rcp_approx(safe);
+#pragma unroll
+    for (int e = 0; e < E; ++e) inc[e] = z[e] * f;
+  }
+}
+
+// One uniform per (ladder, sweep, pair) on a separate Philox key.
+__device__ __forceinline__ float swap_uniform(const KernelArgs& a, unsigned long long ladder_gid, unsigned long long round,
+                                              int pair) {
+  const uint4 r = philox4x32_10((uint32_t)round, ((uint32_t)(round >> 32) & 0xffffu) | ((uint32_t)(pair >> 2) << 16),
+                                (uint32_t)ladder_gid, (uint32_t)(ladder_gid >> 32), a.key0 ^ 0x5851F42Du,
+                                a.key1 ^ 0x4C957F2Du);
+  const int q = pair & 3;
+  const uint32_t w = q == 0 ? r.x : (q == 1 ? r.y : (q == 2 ? r.z : r.w));
+  return u01_from_bits(w);
+}
+
+// pt_rwm_gpu_optimized.py:42-47, literal order; p = min(1, exp(.)), accept iff u < p (:617-621)
+template <bool IEEE>
+__device__ __forceinline__ bool swap_accept(float bj, float bk, float lj, float lk, float u) {
+  using M = Mth<IEEE>;
+  const float l = M::sub(M::sub(M::add(M::mul(bj, lk), M::mul(bk, lj)), M::mul(bj, lj)), M::mul(bk, lk));
+  const float p = fminf(1.0f, M::exp(l));
+  return u < p;  // NaN -> false
+}
+
+template <template <int, bool> class Target, int E, bool IEEE>
+__global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a) {
+  using M = Mth<IEEE>;
+  extern __shared__ float smem[];
+
+  const int W = a.W, K = a.K, d = a.dim;
+  const int cl = threadIdx.x / W;  // chain within CTA
+  Ctx c;
+  c.P = a.P; c.d = d; c.W = W;
+  c.sub = threadIdx.x % W;
+  c.base = c.sub * E;
+  c.lane = threadIdx.x & 31;
+  c.leader = c.lane & ~(W - 1);
+
+  const bool in_cta = cl < a.chains_per_cta;
+  const long long chain_raw = (long long)blockIdx.x * a.chains_per_cta + cl;
+  const bool valid = in_cta && chain_raw < a.n_chains;
+  const long long chain = valid ? chain_raw : 0;  // dummy threads shadow chain 0 but never write
+  const int temp = cl % K;  // chains_per_cta is a multiple of K, so this is also chain % K
+  const long long ladder = chain / K;
+  const bool lead = valid && c.sub == 0;
+  const unsigned long long chain_gid = (unsigned long long)(a.chain_id_base + chain);
+  const unsigned long long ladder_gid = (unsigned long long)(a.chain_id_base / K + ladder);
+
+  Target<E, IEEE> tgt;
+  tgt.init(c);
+
+  float x[E], dscale[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = c.base + e;
+    x[e] = (i < d) ? a.state[chain * d + i] : 0.0f;
+    dscale[e] = (i < d && a.prop_dim_scale) ? a.prop_dim_scale[i] : 1.0f;
+  }
+  float lp = a.logp[chain];
+  const float beta = a.beta[chain];
+  const float scale = a.prop_scale ? a.prop_scale[chain] : 1.0f;
+
+  // shared memory carve-up for the swap sweep
+  float* s_lp = smem;                                  // [chains_per_cta]
+  int* s_src = (int*)(smem + a.chains_per_cta);        // [chains_per_cta]
+  int* s_ok = s_src + a.chains_per_cta;                // [chains_per_cta]
+  float* s_beta = (float*)(s_ok + a.chains_per_cta);   // [chains_per_cta]
+  float* s_x = s_beta + a.chains_per_cta;              // [chains_per_cta, d]
+  if (K > 1) {
+    if (in_cta && c.sub == 0) s_beta[cl] = beta;
+    __syncthreads();
+  }
+
+  // countdowns (no per-step modulo)
+  const long long s_first = a.step_offset + 1;
+  long long swap_cd = -1;
+  if (K > 1) {
+    long long nxt = ((s_first + a.swap_every - 1) / a.swap_every) * a.swap_every;
+    while (nxt <= a.burn_in) nxt += a.swap_every;
+    swap_cd = nxt - s_first;
+  }
+  long long store_cd = -1, store_m = 0;
+  const bool storing = a.samples != nullptr && (a.store_mode == RWMPT_STORE_ALL || (a.store_mode == RWMPT_STORE_COLD && temp == 0));
+  if (a.samples != nullptr) {
+    const long long r = s_first - a.store_start;
+    long long nxt = r <= 0 ? a.store_start + a.thin : s_first + ((a.thin - r % a.thin) % a.thin);
+    store_cd = nxt - s_first;
+    store_m = (nxt - a.store_start) / a.thin - 1;
+  }
+  const long long store_chain = a.store_mode == RWMPT_STORE_ALL ? chain : ladder;
+
+  unsigned long long n_acc = 0, n_swap_acc = 0, last_attempt = 0;
+  long long round_local = 0;
+  float jump_f = 0.0f;
+  double jump_d = 0.0;
+
+  for (long long t = 0; t < a.n_steps; ++t) {
+    const long long s = s_first + t;
+    // 1. proposal increments + accept uniform
+    float inc[E], u;
+    if (a.inj_inc != nullptr) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = c.base + e;
+        inc[e] = (i < d) ? a.inj_inc[(t * a.n_chains + chain) * d + i] : 0.0f;
+      }
+      u = a.inj_u[t * a.n_chains + chain];
+    } else {
+      draw_increments<E, IEEE>(a, c, inc, u, (unsigned long long)s, chain_gid, scale, dscale);
+    }
+    // 2. proposal, 3. its log-density
+    float prop[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) prop[e] = (c.base + e < d) ? M::add(x[e], inc[e]) : 0.0f;
+    const float lpp = tgt.logp(prop, c);
+    // 4. accept rule (rwm_gpu_optimized.py:22-25): NaN compares false -> reject
+    const float lar = M::mul(beta, M::sub(lpp, lp));
+    const bool acc = (lar > 0.0f) || (u < M::exp(lar));
+    // 5. select
+    float xo[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      xo[e] = x[e];
+      x[e] = acc ? prop[e] : x[e];
+    }
+    lp = acc ? lpp : lp;
+    const bool post = s > a.burn_in;
+    if (post) n_acc += acc ? 1u : 0u;
+    if (a.decisions != nullptr && lead) a.decisions[t * a.n_chains + chain] = acc ? 1 : 0;
+
+    // 6. adjacent-temperature sweep (whole ladder is in this CTA)
+    if (K > 1) {
+      if (swap_cd == 0) {
+        swap_cd = a.swap_every;
+        if (in_cta) {
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            if (c.base + e < d) s_x[cl * d + c.base + e] = x[e];
+          if (c.sub == 0) { s_lp[cl] = lp; s_src[cl] = cl; s_ok[cl] = 0; }
+        }
+        __syncthreads();
+        const unsigned long long round_g = (unsigned long long)(a.rounds_before + round_local);  // 0-based
+        const long long su_base = (round_local * a.n_ladders + ladder) * (K - 1);
+        if (a.swap_mode == RWMPT_SWAP_REFERENCE) {
+          // decisions of all pairs are independent here: pair j only ever rewrites slot j
+          bool ok = false;
+          if (valid && temp < K - 1) {
+            const float us = a.inj_su ? a.inj_su[su_base + temp] : swap_uniform(a, ladder_gid, round_g, temp);
+            ok = swap_accept<IEEE>(beta, s_beta[cl + 1], s_lp[cl], s_lp[cl + 1], us);
+            if (ok) {
+#pragma unroll
+              for (int e = 0; e < E; ++e)
+                if (c.base + e < d) x[e] = s_x[(cl + 1) * d + c.base + e];
+              lp = s_lp[cl + 1];
+            }
+            if (lead && a.swap_dec) a.swap_dec[su_base + temp] = ok ? 1 : 0;
+          }
+          if (ok) { n_swap_acc++; last_attempt = round_g * (unsigned long long)(K - 1) + temp + 1; }
+        } else {
+          // textbook exchange: sequential sweep by the ladder's first thread, then everyone gathers
+          if (valid && temp == 0 && c.sub == 0) {
+            for (int j = 0; j < K - 1; ++j) {
+              const int sa = s_src[cl + j], sb = s_src[cl + j + 1];
+              const float us = a.inj_su ? a.inj_su[su_base + j] : swap_uniform(a, ladder_gid, round_g, j);
+              const bool ok = swap_accept<IEEE>(s_beta[cl + j], s_beta[cl + j + 1], s_lp[sa], s_lp[sb], us);
+              if (ok) { s_src[cl + j] = sb; s_src[cl + j + 1] = sa; }
+              s_ok[cl + j] = ok ? 1 : 0;
+              if (a.swap_dec) a.swap_dec[su_base + j] = ok ? 1 : 0;
+            }
+          }
+          __syncthreads();
+          if (valid) {
+            const int src = s_src[cl];
+            if (src != cl) {
+#pragma unroll
+              for (int e = 0; e < E; ++e)
+                if (c.base + e < d) x[e] = s_x[src * d + c.base + e];
+              lp = s_lp[src];
+            }
+            if (temp < K - 1 && s_ok[cl]) { n_swap_acc++; last_attempt = round_g * (unsigned long long)(K - 1) + temp + 1; }
+          }
+        }
+        round_local++;
+        __syncthreads();  // s_x / s_lp are rewritten at the next sweep
+      }
+      swap_cd--;
+    }
+
+    // 7. squared jump of this step (Metropolis move + swap move), s > burn_in
+    if (post) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float dx = M::sub(x[e], xo[e]);
+        jump_f = fmaf(dx, dx, jump_f);
+      }
+      if ((t & 63) == 63) { jump_d += (double)jump_f; jump_f = 0.0f; }
+    }
+
+    // 8. retained samples: layout (chain, row, dim)
+    if (a.samples != nullptr) {
+      if (store_cd == 0) {
+        store_cd = a.thin;
+        if (storing && valid && store_m < a.sample_rows) {
+          float* dst = a.samples + (store_chain * a.sample_stride + store_m) * d;
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            if (c.base + e < d) dst[c.base + e] = x[e];
+          if (a.sample_logp && c.sub == 0) a.sample_logp[store_chain * a.sample_stride + store_m] = lp;
+        }
+        store_m++;
+      }
+      store_cd--;
+    }
+  }
+
+  // epilogue: state, log-density, accumulators
+  jump_d += (double)jump_f;
+  jump_d = group_sum_f64(jump_d, W);
+  if (valid) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (c.base + e < d) a.state[chain * d + c.base + e] = x[e];
+    if (c.sub == 0) {
+      a.logp[chain] = lp;
+      if (a.accept_count) a.accept_count[chain] += n_acc;
+      if (a.sq_jump_sum) a.sq_jump_sum[chain] += jump_d;
+      if (K > 1 && temp < K - 1 && a.swap_accepts) a.swap_accepts[ladder * (K - 1) + temp] += n_swap_acc;
+      if (K > 1 && a.swap_last_attempt && last_attempt > a.swap_last_attempt[chain]) a.swap_last_attempt[chain] = last_attempt;
+    }
+  }
+}
+
+// ---- batched log-density kernel (rwmpt_log_density) -------------------------------------------
+template <template <int, bool> class Target, int E, bool IEEE>
+__global__ void __launch_bounds__(kMaxCtaThreads) logp_kernel(const float* __restrict__ P, int d, int W, const float* __restrict__ x,
+                                                              long long n, float* __restrict__ out) {
+  const int per_cta = blockDim.x / W;
+  const int cl = threadIdx.x / W;
+  Ctx c;
+  c.P = P; c.d = d; c.W = W;
+  c.sub = threadIdx.x % W;
+  c.base = c.sub * E;
+  c.lane = threadIdx.x & 31;
+  c.leader = c.lane & ~(W - 1);
+  Target<E, IEEE> tgt;
+  tgt.init(c);
+  const long long stride = (long long)gridDim.x * per_cta;
+  const long long n_round = ((n + stride - 1) / stride) * stride;  // keep warps converged for the shuffles
+  for (long long r = (long long)blockIdx.x * per_cta + cl; r < n_round; r += stride) {
+    const bool ok = r < n;
+    float v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      v[e] = (ok && i < d) ? x[r * d + i] : 0.0f;
+    }
+    const float lp = tgt.logp(v, c);
+    if (ok && c.sub == 0) out[r] = lp;
+  }
+}
+
+// Host-side launchers instantiated per target family in rwmpt_inst_*.cu
+struct LaunchGeom {
+  int E;
+  int W;
+  int threads;
+  int chains_per_cta;
+  long long grid;
+  size_t smem;
+};
+
+}  // namespace rwmpt

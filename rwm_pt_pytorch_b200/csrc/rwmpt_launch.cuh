@@ -1,0 +1,104 @@
+// rwmpt_launch.cuh -- host-side launch helpers; each rwmpt_inst_<family>.cu instantiates one target family
+// for every supported elements-per-lane count, so the families compile in parallel.
+#pragma once
+
+#include "rwmpt_kernel.cuh"
+
+namespace rwmpt {
+
+// elements-per-lane (E) variants compiled for each math mode; the picker in rwmpt_api.cu uses the same lists
+#define RWMPT_FAST_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
+#define RWMPT_IEEE_E_LIST(X) X(1) X(2) X(5) X(13)
+
+template <template <int, bool> class Target, int E, bool IEEE>
+cudaError_t launch_mcmc_one(const KernelArgs& a, const LaunchGeom& g, cudaStream_t st) {
+  auto kern = mcmc_kernel<Target, E, IEEE>;
+  if (g.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<(unsigned)g.grid, g.threads, g.smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <template <int, bool> class Target, int E, bool IEEE>
+cudaError_t launch_logp_one(const float* P, int d, int W, const float* x, long long n, float* out, cudaStream_t st) {
+  const int threads = 128;
+  const int per_cta = threads / W;
+  long long blocks = (n + per_cta - 1) / per_cta;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  logp_kernel<Target, E, IEEE><<<(unsigned)blocks, threads, 0, st>>>(P, d, W, x, n, out);
+  return cudaGetLastError();
+}
+
+template <template <int, bool> class Target>
+cudaError_t launch_mcmc_family(const KernelArgs& a, const LaunchGeom& g, bool ieee, cudaStream_t st) {
+  if (ieee) {
+    switch (g.E) {
+#define X(e) case e: return launch_mcmc_one<Target, e, true>(a, g, st);
+      RWMPT_IEEE_E_LIST(X)
+#undef X
+    }
+  } else {
+    switch (g.E) {
+#define X(e) case e: return launch_mcmc_one<Target, e, false>(a, g, st);
+      RWMPT_FAST_E_LIST(X)
+#undef X
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <template <int, bool> class Target>
+cudaError_t launch_logp_family(const float* P, int d, int E, int W, const float* x, long long n, float* out, bool ieee,
+                               cudaStream_t st) {
+  if (ieee) {
+    switch (E) {
+#define X(e) case e: return launch_logp_one<Target, e, true>(P, d, W, x, n, out, st);
+      RWMPT_IEEE_E_LIST(X)
+#undef X
+    }
+  } else {
+    switch (E) {
+#define X(e) case e: return launch_logp_one<Target, e, false>(P, d, W, x, n, out, st);
+      RWMPT_FAST_E_LIST(X)
+#undef X
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+// one pair of entry points per family, defined in rwmpt_inst_<family>.cu
+#define RWMPT_FAMILY_LIST(X)                 \
+  X(rough_carpet, RoughCarpet)               \
+  X(three_mixture, ThreeMixture)             \
+  X(full_rosenbrock, FullRosenbrock)         \
+  X(even_rosenbrock, EvenRosenbrock)         \
+  X(hybrid_rosenbrock, HybridRosenbrock)     \
+  X(neal_funnel, NealFunnel)                 \
+  X(hypercube, Hypercube)                    \
+  X(iid_gamma, IIDGamma)                     \
+  X(iid_beta, IIDBeta)                       \
+  X(scaled_mvn, ScaledMVN)                   \
+  X(mvn_diag, MVNDiag)
+
+#define X(name, cls)                                                                                         \
+  cudaError_t launch_mcmc_##name(const KernelArgs& a, const LaunchGeom& g, bool ieee, cudaStream_t st);       \
+  cudaError_t launch_logp_##name(const float* P, int d, int E, int W, const float* x, long long n, float* out, \
+                                 bool ieee, cudaStream_t st);
+RWMPT_FAMILY_LIST(X)
+#undef X
+
+#define RWMPT_DEFINE_FAMILY(name, cls)                                                                        \
+  namespace rwmpt {                                                                                           \
+  cudaError_t launch_mcmc_##name(const KernelArgs& a, const LaunchGeom& g, bool ieee, cudaStream_t st) {      \
+    return launch_mcmc_family<cls>(a, g, ieee, st);                                                           \
+  }                                                                                                           \
+  cudaError_t launch_logp_##name(const float* P, int d, int E, int W, const float* x, long long n, float* out, \
+                                 bool ieee, cudaStream_t st) {                                                \
+    return launch_logp_family<cls>(P, d, E, W, x, n, out, ieee, st);                                          \
+  }                                                                                                           \
+  }
+
+}  // namespace rwmpt

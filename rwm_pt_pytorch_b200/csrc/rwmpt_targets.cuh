@@ -1,0 +1,387 @@
+// rwmpt_targets.cuh -- target log-densities as device functors, one per family of
+// target_distributions/*_torch.py.  A chain's d coordinates are spread over W lanes, E per lane
+// (blocked: lane `sub` holds coordinates [sub*E, sub*E+E)); each functor computes its lane-partial
+// and reduces over the chain's lanes with XOR butterflies, returning the same value on every lane.
+//
+// IEEE = true reproduces the reference's fp32 operation order (SURVEY.md section 8a') with un-fused,
+// correctly-rounded operations; IEEE = false is the throughput path (MUFU ex2/lg2, FMA, fewer logs).
+#pragma once
+
+#include "rwmpt_common.cuh"
+
+namespace rwmpt {
+
+#define RWMPT_NEG_INF (__int_as_float(0xff800000))
+
+// ---- RoughCarpetDistributionTorch.log_density, multimodal_torch.py:470-510 ---------------------
+template <int E, bool IEEE>
+struct RoughCarpet {
+  using M = Mth<IEEE>;
+  float m0, m1, m2, lw0, lw1, lw2, lsp, J;
+  float a0, a1, a2;  // fast path: (lw_k - lsp) * log2(e)
+  bool has_s;
+  float s[E];
+
+  __device__ __forceinline__ void init(const Ctx& c) {
+    const float* P = c.P;
+    m0 = P[0]; m1 = P[1]; m2 = P[2];
+    lw0 = P[3]; lw1 = P[4]; lw2 = P[5];
+    lsp = P[6];
+    has_s = P[7] != 0.0f;
+    J = has_s ? P[8] : 0.0f;
+    a0 = (lw0 - lsp) * kLog2e; a1 = (lw1 - lsp) * kLog2e; a2 = (lw2 - lsp) * kLog2e;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      s[e] = (has_s && i < c.d) ? P[RWMPT_PARAM_HEADER + i] : 1.0f;
+    }
+  }
+
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    if constexpr (IEEE) {
+      float part = 0.0f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float xs = has_s ? M::mul(x[e], s[e]) : x[e];
+        const float t0 = M::add(M::sub(M::mul(-0.5f, M::sq(M::sub(xs, m0))), lsp), lw0);
+        const float t1 = M::add(M::sub(M::mul(-0.5f, M::sq(M::sub(xs, m1))), lsp), lw1);
+        const float t2 = M::add(M::sub(M::mul(-0.5f, M::sq(M::sub(xs, m2))), lsp), lw2);
+        float mx = fmaxf(fmaxf(t0, t1), t2);
+        if (isinf(mx)) mx = 0.0f;  // torch.logsumexp masks infinite maxima
+        const float ss = M::add(M::add(M::exp(M::sub(t0, mx)), M::exp(M::sub(t1, mx))), M::exp(M::sub(t2, mx)));
+        const float L = M::add(M::log(ss), mx);
+        if (c.base + e < c.d) part = M::add(part, L);
+      }
+      return M::add(group_sum(part, c.W), J);
+    } else {
+      // work in base 2; sum_i log(sum_k exp(t_ik)) = sum_i max_i + log(prod_i sum_k exp(t_ik - max_i)):
+      // one lg2 per lane instead of one per coordinate.
+      float hi = 0.0f, prod = 1.0f;
+      constexpr float h = -0.5f * kLog2e;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float xs = x[e] * s[e];
+        const float d0 = xs - m0, d1 = xs - m1, d2 = xs - m2;
+        const float t0 = fmaf(d0 * h, d0, a0), t1 = fmaf(d1 * h, d1, a1), t2 = fmaf(d2 * h, d2, a2);
+        const float mx = fmaxf(fmaxf(t0, t1), t2);
+        const float ss = ex2_approx(t0 - mx) + ex2_approx(t1 - mx) + ex2_approx(t2 - mx);
+        if (c.base + e < c.d) {
+          hi += mx;
+          prod *= ss;
+        }
+      }
+      const float part = (hi + lg2_approx(prod)) * kLn2;
+      return group_sum(part, c.W) + J;
+    }
+  }
+};
+
+// ---- ThreeMixtureDistributionTorch.log_density, multimodal_torch.py:173-242 --------------------
+template <int E, bool IEEE>
+struct ThreeMixture {
+  using M = Mth<IEEE>;
+  float lw[3], c1[3], J;
+  bool scaled;
+  float mu[3][E];
+  float s[E];
+
+  __device__ __forceinline__ void init(const Ctx& c) {
+    const float* P = c.P;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lw[k] = P[k]; c1[k] = P[3 + k]; }
+    scaled = P[6] != 0.0f;
+    J = P[7];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      const bool ok = i < c.d;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mu[k][e] = ok ? P[RWMPT_PARAM_HEADER + k * c.d + i] : 0.0f;
+      s[e] = (ok && scaled) ? P[RWMPT_PARAM_HEADER + 3 * c.d + i] : 1.0f;
+    }
+  }
+
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    float q[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float xs = scaled ? M::mul(x[e], s[e]) : x[e];
+      if (c.base + e < c.d) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float dd = M::sub(xs, mu[k][e]);
+          q[k] = IEEE ? M::add(q[k], M::mul(dd, dd)) : fmaf(dd, dd, q[k]);
+        }
+      }
+    }
+    float t[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float qq = group_sum(q[k], c.W);
+      float v = M::add(M::mul(-0.5f, qq), c1[k]);
+      if (scaled) v = M::add(v, J);
+      t[k] = M::add(v, lw[k]);
+    }
+    float mx = fmaxf(fmaxf(t[0], t[1]), t[2]);
+    if (isinf(mx)) mx = 0.0f;
+    const float ss = M::add(M::add(M::exp(M::sub(t[0], mx)), M::exp(M::sub(t[1], mx))), M::exp(M::sub(t[2], mx)));
+    return M::add(M::log(ss), mx);
+  }
+};
+
+// ---- FullRosenbrockTorch.log_density, rosenbrock_torch.py:67-84 --------------------------------
+template <int E, bool IEEE>
+struct FullRosenbrock {
+  using M = Mth<IEEE>;
+  float a, b;
+  float mu[E];
+
+  __device__ __forceinline__ void init(const Ctx& c) {
+    a = c.P[0]; b = c.P[1];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      mu[e] = (i < c.d - 1) ? c.P[RWMPT_PARAM_HEADER + i] : 0.0f;
+    }
+  }
+
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    const float xn_lane = from_next_lane(x[0]);  // x[(sub+1)*E]; masked below when it does not exist
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float xn = (e + 1 < E) ? x[(e + 1 < E) ? e + 1 : e] : xn_lane;
+      const float r = M::sub(xn, M::sq(x[e]));
+      const float t1 = M::mul(b, M::sq(r));
+      const float t2 = M::mul(a, M::sq(M::sub(x[e], mu[e])));
+      if (c.base + e < c.d - 1) {
+        s1 = M::add(s1, t1);
+        s2 = M::add(s2, t2);
+      }
+    }
+    if constexpr (IEEE) {
+      return -M::add(group_sum(s1, c.W), group_sum(s2, c.W));
+    } else {
+      return -group_sum(s1 + s2, c.W);
+    }
+  }
+};
+
+// ---- EvenRosenbrockTorch.log_density, rosenbrock_torch.py:194-210 ------------------------------
+template <int E, bool IEEE>
+struct EvenRosenbrock {
+  using M = Mth<IEEE>;
+  float a, b;
+  float mu[E];
+
+  __device__ __forceinline__ void init(const Ctx& c) {
+    a = c.P[0]; b = c.P[1];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      mu[e] = (i < c.d && (i & 1) == 0) ? c.P[RWMPT_PARAM_HEADER + (i >> 1)] : 0.0f;
+    }
+  }
+
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    const float xn_lane = from_next_lane(x[0]);
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      const float xn = (e + 1 < E) ? x[(e + 1 < E) ? e + 1 : e] : xn_lane;
+      const float t1 = M::mul(a, M::sq(M::sub(x[e], mu[e])));
+      const float t2 = M::mul(b, M::sq(M::sub(xn, M::sq(x[e]))));
+      if ((i & 1) == 0 && i + 1 < c.d) {
+        s1 = M::add(s1, t1);
+        s2 = M::add(s2, t2);
+      }
+    }
+    if constexpr (IEEE) {
+      return -M::add(group_sum(s1, c.W), group_sum(s2, c.W));
+    } else {
+      return -group_sum(s1 + s2, c.W);
+    }
+  }
+};
+
+// ---- HybridRosenbrockTorch.log_density, rosenbrock_torch.py:312-351 ----------------------------
+template <int E, bool IEEE>
+struct HybridRosenbrock {
+  using M = Mth<IEEE>;
+  float a, b, mu;
+  unsigned first_mask;  // bit e set: coordinate is the first of its block (depends on x_0^2)
+  unsigned valid_mask;  // bit e set: coordinate index in [1, d)
+
+  __device__ __forceinline__ void init(const Ctx& c) {
+    a = c.P[0]; b = c.P[1]; mu = c.P[2];
+    const int n1 = (int)c.P[3];
+    const int blk = n1 - 1;
+    first_mask = 0; valid_mask = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      if (i >= 1 && i < c.d) {
+        valid_mask |= 1u << e;
+        if ((i - 1) % blk == 0) first_mask |= 1u << e;
+      }
+    }
+  }
+
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    const float x0 = from_leader(x[0], c);
+    const float xp_lane = from_prev_lane(x[E - 1]);
+    const float x0sq = M::sq(x0);
+    float part = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float prev = (e > 0) ? x[(e > 0) ? e - 1 : 0] : xp_lane;
+      const float ref = ((first_mask >> e) & 1u) ? x0sq : M::sq(prev);
+      const float t = M::mul(b, M::sq(M::sub(x[e], ref)));
+      if ((valid_mask >> e) & 1u) part = M::add(part, t);
+    }
+    const float head = M::mul(-a, M::sq(M::sub(x0, mu)));
+    return M::sub(head, group_sum(part, c.W));
+  }
+};
+
+// ---- NealFunnelTorch.log_density, funnel_torch.py:39-76 ----------------------------------------
+template <int E, bool IEEE>
+struct NealFunnel {
+  using M = Mth<IEEE>;
+  float mu_v, sv, mu_z, lsv, l2p, dm1;
+
+  __device__ __forceinline__ void init(const Ctx& c) {
+    mu_v = c.P[0]; sv = c.P[1]; mu_z = c.P[2]; lsv = c.P[3]; l2p = c.P[4]; dm1 = c.P[5];
+  }
+
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    const float v = from_leader(x[0], c);
+    float q = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      const float dz = M::sub(x[e], mu_z);
+      if (i >= 1 && i < c.d) q = IEEE ? M::add(q, M::mul(dz, dz)) : fmaf(dz, dz, q);
+    }
+    q = group_sum(q, c.W);
+    const float prior = M::sub(M::sub(M::mul(-0.5f, l2p), M::mul(0.5f, lsv)),
+                               M::div(M::mul(0.5f, M::sq(M::sub(v, mu_v))), sv));
+    if (c.d == 1) return prior;
+    const float lik = M::sub(M::sub(M::mul(M::mul(-0.5f, dm1), l2p), M::mul(M::mul(0.5f, dm1), v)),
+                             M::mul(M::mul(0.5f, M::exp(-v)), q));
+    return M::add(prior, lik);
+  }
+};
+
+// ---- HypercubeTorch.log_density, hypercube_torch.py:49-80 --------------------------------------
+template <int E, bool IEEE>
+struct Hypercube {
+  float L, R, lud;
+  __device__ __forceinline__ void init(const Ctx& c) { L = c.P[0]; R = c.P[1]; lud = c.P[2]; }
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    float outside = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (c.base + e < c.d && !(x[e] >= L && x[e] <= R)) outside += 1.0f;
+    return group_sum(outside, c.W) == 0.0f ? lud : RWMPT_NEG_INF;
+  }
+};
+
+// ---- IIDGammaTorch.log_density, iid_product_torch.py:52-91 -------------------------------------
+template <int E, bool IEEE>
+struct IIDGamma {
+  using M = Mth<IEEE>;
+  float k, th, lnc;
+  __device__ __forceinline__ void init(const Ctx& c) { k = c.P[0]; th = c.P[1]; lnc = c.P[2]; }
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    float part = 0.0f;
+    const float km1 = M::sub(k, 1.0f);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (c.base + e < c.d) {
+        const bool ok = x[e] > 0.0f;
+        const float xx = ok ? x[e] : 1.0f;
+        const float t = M::sub(M::mul(km1, M::log(xx)), M::div(xx, th));
+        part = ok ? M::add(part, t) : RWMPT_NEG_INF;
+      }
+    }
+    return M::sub(group_sum(part, c.W), lnc);
+  }
+};
+
+// ---- IIDBetaTorch.log_density, iid_product_torch.py:188-229 ------------------------------------
+template <int E, bool IEEE>
+struct IIDBeta {
+  using M = Mth<IEEE>;
+  float al, be, lnc;
+  __device__ __forceinline__ void init(const Ctx& c) { al = c.P[0]; be = c.P[1]; lnc = c.P[2]; }
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    float part = 0.0f;
+    const float am1 = M::sub(al, 1.0f), bm1 = M::sub(be, 1.0f);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (c.base + e < c.d) {
+        const bool ok = x[e] > 0.0f && x[e] < 1.0f;
+        const float xx = ok ? x[e] : 0.5f;
+        const float t = M::add(M::mul(am1, M::log(xx)), M::mul(bm1, M::log(M::sub(1.0f, xx))));
+        part = ok ? M::add(part, t) : RWMPT_NEG_INF;
+      }
+    }
+    return M::add(group_sum(part, c.W), lnc);
+  }
+};
+
+// ---- ScaledMultivariateNormalTorch.log_density, multivariate_normal_torch.py:198-223 -----------
+template <int E, bool IEEE>
+struct ScaledMVN {
+  using M = Mth<IEEE>;
+  float lnc;
+  float cc[E];
+  __device__ __forceinline__ void init(const Ctx& c) {
+    lnc = c.P[0];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      cc[e] = (i < c.d) ? c.P[RWMPT_PARAM_HEADER + i] : 0.0f;
+    }
+  }
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    float part = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float sx = M::mul(cc[e], x[e]);
+      if (c.base + e < c.d) part = IEEE ? M::add(part, M::mul(sx, sx)) : fmaf(sx, sx, part);
+    }
+    return M::sub(lnc, M::mul(0.5f, group_sum(part, c.W)));
+  }
+};
+
+// ---- MultivariateNormalTorch.log_density with diagonal covariance, multivariate_normal_torch.py:62-92
+template <int E, bool IEEE>
+struct MVNDiag {
+  using M = Mth<IEEE>;
+  float lnc;
+  float mean[E], prec[E];
+  __device__ __forceinline__ void init(const Ctx& c) {
+    lnc = c.P[0];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      mean[e] = (i < c.d) ? c.P[RWMPT_PARAM_HEADER + i] : 0.0f;
+      prec[e] = (i < c.d) ? c.P[RWMPT_PARAM_HEADER + c.d + i] : 0.0f;
+    }
+  }
+  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+    float part = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float cen = M::sub(x[e], mean[e]);
+      const float t = M::mul(M::mul(cen, prec[e]), cen);
+      if (c.base + e < c.d) part = M::add(part, t);
+    }
+    return M::add(M::mul(-0.5f, group_sum(part, c.W)), lnc);
+  }
+};
+
+}  // namespace rwmpt
