@@ -173,6 +173,10 @@ int rwmpt_pt_swap(float* state, float* logp, const float* beta, int64_t n_ladder
 int rwmpt_esjd_reduce(const float* samples, int64_t n_chains, int64_t stride, int64_t first, int64_t n, int32_t dim,
                       double* esjd_out, unsigned long long* moved_out, void* cuda_stream);
 
+/* Measures this GPU's FP32 FFMA and SFU (MUFU.EX2) issue peaks with dependent-free loops (synchronous; a few ms):
+ * the denominators of the FP32 / SFU rooflines of SURVEY.md section 8(d).  fp32_tflops counts an FMA as 2 flops. */
+int rwmpt_probe_peaks(double* fp32_tflops, double* sfu_gops);
+
 /* Philox4x32-10 known-answer hook (host in / host out, runs one device thread). */
 int rwmpt_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

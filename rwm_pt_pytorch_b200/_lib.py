@@ -71,6 +71,8 @@ def _declare(lib):
     lib.rwmpt_pt_swap.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, u64, i64, i64, vp, vp, vp]
     lib.rwmpt_esjd_reduce.argtypes = [vp, i64, i64, i64, i64, i32, vp, vp, vp]
     lib.rwmpt_debug_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.rwmpt_probe_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.rwmpt_probe_peaks.restype = C.c_int
     lib.rwmpt_run_host.argtypes = [C.POINTER(RunArgs), i32, C.POINTER(u64), C.POINTER(u64)]
     for name in ("rwmpt_rwm_run", "rwmpt_pt_run", "rwmpt_pick_lanes", "rwmpt_log_density", "rwmpt_proposal_sample",
                  "rwmpt_pt_swap", "rwmpt_esjd_reduce", "rwmpt_debug_philox", "rwmpt_run_host"):
@@ -136,4 +138,4 @@ def exported_symbols():
     """Names declared in include/rwmpt.h (used by the CPU test that checks the library exports them all)."""
     return ["rwmpt_version", "rwmpt_last_error", "rwmpt_sizeof_run_args", "rwmpt_rwm_run", "rwmpt_pt_run",
             "rwmpt_count_swap_rounds", "rwmpt_pick_lanes", "rwmpt_log_density", "rwmpt_proposal_sample",
-            "rwmpt_pt_swap", "rwmpt_esjd_reduce", "rwmpt_debug_philox", "rwmpt_run_host"]
+            "rwmpt_pt_swap", "rwmpt_esjd_reduce", "rwmpt_probe_peaks", "rwmpt_debug_philox", "rwmpt_run_host"]

@@ -78,7 +78,7 @@ static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_
     for (int k = 0; k < n_list; ++k) {
       const int E = list[k];
       if ((long long)E * W < d) continue;
-      if (W > 1 && (long long)(W - 1) * E >= d) continue;
+      if (want_W <= 0 && W > 1 && (long long)(W - 1) * E >= d) continue;  // auto mode: no lane that is all padding
       const double waste = (double)E * W / d;
       const double threads = (double)n_chains * W;
       double score = waste;
@@ -340,6 +340,42 @@ __global__ void __launch_bounds__(256) esjd_kernel(const float* __restrict__ sam
   }
 }
 
+// ---- peak probes: dependent-free FFMA and MUFU.EX2 loops, 8 independent chains per thread ---------
+__global__ void __launch_bounds__(256) probe_ffma_kernel(float* out, int iters) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 1e-3f * (threadIdx.x + i);
+  const float b = 0.999f, c = 1e-4f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], b, c);
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) probe_mufu_kernel(float* out, int iters) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 1e-3f * (threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = ex2_approx(-a[i]);
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;
+}
+
 __global__ void philox_kat_kernel(const uint32_t* in, uint32_t* out) {
   const uint4 r = philox4x32_10(in[0], in[1], in[2], in[3], in[4], in[5]);
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
@@ -449,6 +485,40 @@ int rwmpt_esjd_reduce(const float* samples, int64_t n_chains, int64_t stride, in
   esjd_kernel<<<(unsigned)(n_chains * cpc), 256, 0, st>>>(samples, stride, first, n, dim, cpc, esjd_out, moved_out);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "esjd kernel launch");
+  return RWMPT_OK;
+}
+
+int rwmpt_probe_peaks(double* fp32_tflops, double* sfu_gops) {
+  float* d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_out, sizeof(float));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  const int blocks = 148 * 8, threads = 256;
+  double best[2] = {0.0, 0.0};
+  for (int kind = 0; kind < 2; ++kind) {
+    const int iters = kind == 0 ? 4096 : 1024;
+    for (int rep = 0; rep < 4; ++rep) {
+      cudaEventRecord(t0);
+      if (kind == 0) probe_ffma_kernel<<<blocks, threads>>>(d_out, iters);
+      else probe_mufu_kernel<<<blocks, threads>>>(d_out, iters);
+      cudaEventRecord(t1);
+      e = cudaEventSynchronize(t1);
+      if (e != cudaSuccess) break;
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, t0, t1);
+      const double ops = (double)blocks * threads * (double)iters * 64.0;
+      const double rate = ops / (ms * 1e-3);
+      if (rep > 0 && rate > best[kind]) best[kind] = rate;
+    }
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(e, "peak probe");
+  if (fp32_tflops) *fp32_tflops = 2.0 * best[0] / 1e12;
+  if (sfu_gops) *sfu_gops = best[1] / 1e9;
   return RWMPT_OK;
 }
 

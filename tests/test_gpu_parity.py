@@ -1,0 +1,617 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the CUDA path, called through the Python facade and the
+C ABI, against (a) the golden fixtures produced by the unmodified reference and (b) the NumPy oracle on the same
+seeded inputs.
+
+Bars (BASELINE.json north_star): with injected randomness and math_mode='ieee', accept and swap decisions are
+bit-exact and chain states match (they are x + increment, so exactly) -- a decision may differ only at a *near tie*
+(|u - exp(lar)| <= 2e-5 exp(lar): the fp32 reduction order differs between torch, NumPy and the shuffle butterfly,
+which moves the log-density by an ulp); log-densities agree to 1e-5 relative.  With the native Philox stream,
+acceptance agrees within 3 Monte-Carlo standard errors and ESJD within 2 %.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rwmpt_oracle as O
+from tests._util import (load_golden, golden_names, product_target, target_key_of, near_tie_report, PHILOX_KAT)
+
+pytestmark = pytest.mark.gpu
+
+NEAR_TIE_REL = 2e-5
+LOGP_RTOL, LOGP_ATOL = 1e-5, 2e-5
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _close_logp(a, b, rtol=LOGP_RTOL, atol=LOGP_ATOL):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    with np.errstate(invalid="ignore"):
+        ok = both_inf | (np.abs(a - b) <= atol + rtol * np.abs(b))
+    assert ok.all(), f"max abs diff {np.nanmax(np.abs(np.where(both_inf, 0, a - b)))} at {np.argwhere(~ok)[:5]}"
+
+
+def _algs():
+    from rwm_pt_pytorch_b200.algorithms import RandomWalkMH_GPU_Optimized, ParallelTemperingRWM_GPU_Optimized
+    return RandomWalkMH_GPU_Optimized, ParallelTemperingRWM_GPU_Optimized
+
+
+# --------------------------------------------------------------------------------------------------------
+def test_philox_known_answers_device():
+    import ctypes as C
+    from rwm_pt_pytorch_b200 import _lib
+    _cuda()
+    lib = _lib.load()
+    for ctr, key, want in PHILOX_KAT:
+        out = (C.c_uint32 * 4)()
+        _lib.check(lib.rwmpt_debug_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out))
+        assert list(out) == want
+
+
+@pytest.mark.parametrize("mode", ["ieee", "fast"])
+@pytest.mark.parametrize("name", golden_names("logp_"))
+def test_log_density_golden(name, mode):
+    dev = _cuda()
+    spec, g = load_golden(name)
+    t = product_target(target_key_of(name))
+    t.math_mode = mode
+    try:
+        lp = t.log_density(torch.tensor(g["x"], device=dev)).cpu().numpy()
+        tol = dict(rtol=LOGP_RTOL, atol=LOGP_ATOL) if mode == "ieee" else dict(rtol=2e-4, atol=2e-3)
+        _close_logp(lp, g["logp"], **tol)
+        single = np.stack([t.log_density(torch.tensor(g["x"][i])).cpu().numpy() for i in range(4)])
+        _close_logp(single, g["logp_single"][:4], **tol)
+        assert t.log_density(torch.tensor(g["x"][0])).ndim == 0
+    finally:
+        t.math_mode = "fast"
+
+
+@pytest.mark.parametrize("name", golden_names("rwm_"))
+def test_rwm_injected_matches_reference(name):
+    """Teacher: the reference's own increments / uniforms; the kernel must take the reference's decisions."""
+    dev = _cuda()
+    RWM, _ = _algs()
+    spec, g = load_golden(name)
+    t = product_target(target_key_of(name))
+    T, d = g["increments"].shape
+    burn = int(g["burn_in"])
+    algo = RWM(d, 1.0, t, beta=float(g["beta"]), burn_in=burn, device=dev, pre_allocate_steps=T - burn,
+               math_mode="ieee", initial_states=g["x0"][None])
+    dec = algo.run_injected(g["increments"][:, None], g["uniforms"][:, None]).cpu().numpy()
+    ora = O.rwm_run(spec, g["x0"][None], g["beta"], g["increments"][:, None], g["uniforms"][:, None], burn_in=burn)
+    near, hard, until = near_tie_report(dec, g["decisions"][:, None], ora["lar"], g["uniforms"][:, None], NEAR_TIE_REL)
+    assert hard == 0, f"{hard} decision mismatches that are not near ties"
+    n = int(until[0])
+    chain = algo.get_chain_gpu().cpu().numpy()
+    assert chain.shape == (T + 1, d)
+    np.testing.assert_array_equal(chain[: n + 1], g["chain"][: n + 1])
+    _close_logp(algo.get_log_densities_gpu().cpu().numpy()[: n + 1], g["logp"][: n + 1])
+    if near == 0:
+        assert algo.num_acceptances == int(g["num_acceptances"])
+        assert algo.acceptance_rate == pytest.approx(float(g["acceptance_rate"]), rel=1e-12)
+        assert algo.expected_squared_jump_distance_gpu() == pytest.approx(float(g["esjd"]), rel=1e-5)
+        assert float(algo._batch.sq_jump_sum[0].item()) / (T - burn) == pytest.approx(float(g["esjd"]), rel=1e-5)
+
+
+@pytest.mark.parametrize("name", golden_names("pt_"))
+def test_pt_injected_matches_reference(name):
+    dev = _cuda()
+    _, PT = _algs()
+    spec, g = load_golden(name)
+    t = product_target(target_key_of(name))
+    T, K, d = g["increments"].shape
+    burn, se = int(g["burn_in"]), int(g["swap_every"])
+    algo = PT(d, float(g["var"]), t, beta_ladder=[float(b) for b in g["betas"]], swap_every=se, burn_in=burn, device=dev,
+              pre_allocate_steps=T - burn, math_mode="ieee", swap_mode="reference", initial_states=g["x0"][None])
+    np.testing.assert_array_equal(algo._scales, g["chol_diag"])
+    dec, sdec = algo.run_injected(g["increments"], g["uniforms"], g["swap_uniforms"][:, None])
+    dec, sdec = dec.cpu().numpy(), sdec.cpu().numpy()[:, 0]
+    ora = O.pt_run(spec, g["x0"][None], g["betas"], g["increments"][:, None], g["uniforms"][:, None],
+                   g["swap_uniforms"][:, None], se, burn_in=burn)
+    if np.array_equal(dec, g["decisions"]) and np.array_equal(sdec, g["swap_decisions"]):
+        states = torch.stack(algo.get_all_chains_gpu()).cpu().numpy().transpose(1, 0, 2)     # (T+1, K, d)
+        np.testing.assert_array_equal(states, g["states"])
+        _close_logp(algo.pre_allocated_log_densities.cpu().numpy().T, g["logp"])
+        assert algo.num_swap_attempts == int(g["num_swap_attempts"])
+        assert algo.num_swap_acceptances == int(g["num_swap_acceptances"])
+        assert algo.swap_acceptance_rate == pytest.approx(float(g["swap_acceptance_rate"]), rel=1e-12)
+        assert algo.pt_esjd == pytest.approx(float(g["pt_esjd"]), rel=1e-9)
+        assert algo.squared_jump_distances == pytest.approx(float(g["squared_jump_distances"]), rel=1e-9)
+        assert algo.expected_squared_jump_distance_gpu() == pytest.approx(float(g["cold_esjd"]), rel=1e-5)
+        assert len(algo.chain) == T + 1 and algo.step_counter == T
+    else:
+        # a near tie somewhere: everything before the first differing step must still agree
+        bad_mh = np.argwhere(dec != g["decisions"])
+        bad_sw = np.argwhere(sdec != g["swap_decisions"])
+        first = min([int(bad_mh[0][0])] if len(bad_mh) else [T]) if len(bad_mh) else T
+        if len(bad_sw):
+            rounds = [s for s in range(1, T + 1) if s % se == 0 and s > burn]
+            first = min(first, rounds[int(bad_sw[0][0])] - 1)
+        lar = ora["logp"]  # only used for the message
+        states = torch.stack(algo.get_all_chains_gpu()).cpu().numpy().transpose(1, 0, 2)
+        np.testing.assert_array_equal(states[: first + 1], g["states"][: first + 1])
+        if len(bad_mh) and int(bad_mh[0][0]) == first:
+            tt, kk = int(bad_mh[0][0]), int(bad_mh[0][1])
+            lp_c, lp_p = g["logp"][tt, kk], O.log_density(spec, g["states"][tt, kk] + g["increments"][tt, kk])
+            p = np.exp(np.float64(g["betas"][kk]) * (np.float64(lp_p) - np.float64(lp_c)))
+            assert abs(float(g["uniforms"][tt, kk]) - p) <= 10 * NEAR_TIE_REL * p, "decision mismatch that is not a near tie"
+        pytest.xfail(f"near tie at step {first} (documented: fp32 reduction-order ulp); prefix matches exactly")
+
+
+@pytest.mark.parametrize("case", [
+    ("rough_carpet_d20", 20, 0), ("rough_carpet_d20", 20, 8), ("even_rosenbrock_d20", 20, 2), ("even_rosenbrock_d30", 30, 0),
+    ("full_rosenbrock_d20", 20, 16), ("three_mixture_pm15_d50", 50, 0), ("neal_funnel_d10", 10, 4), ("hybrid_rosenbrock_n3x5", 11, 0),
+    ("iid_gamma_d8", 8, 0), ("iid_beta_d8", 8, 2), ("hypercube_pm1_d5", 5, 1), ("scaled_mvn_d12", 12, 0), ("mvn_diag_d6", 6, 0),
+])
+def test_rwm_batch_matches_oracle(case):
+    """64 chains x 250 steps with seeded NumPy randomness, every lanes-per-chain mapping exercised."""
+    key, d, lanes = case
+    dev = _cuda()
+    RWM, _ = _algs()
+    t = product_target(key)
+    spec = t.spec()
+    rs = np.random.RandomState(hash(key) % 2 ** 31)
+    B, T, burn = 64, 250, 20
+    name = t.get_name()
+    x0 = np.stack([O.initial_state(name, d, rs) for _ in range(B)]).astype(np.float32)
+    scale = {"hypercube_pm1_d5": 0.3, "iid_beta_d8": 0.08, "even_rosenbrock_d20": 0.07, "even_rosenbrock_d30": 0.06,
+             "full_rosenbrock_d20": 0.08, "hybrid_rosenbrock_n3x5": 0.1}.get(key, 0.6)
+    inc = (rs.randn(T, B, d) * scale).astype(np.float32)
+    u = rs.rand(T, B).astype(np.float32)
+    betas = np.linspace(1.0, 0.3, B).astype(np.float32)
+    algo = RWM(d, 1.0, t, beta=betas, burn_in=burn, device=dev, num_chains=B, store="all", math_mode="ieee",
+               initial_states=x0, lanes_per_chain=lanes)
+    dec = algo.run_injected(inc, u).cpu().numpy()
+    ora = O.rwm_run(spec, x0, betas, inc, u, burn_in=burn)
+    near, hard, until = near_tie_report(dec, ora["decisions"], ora["lar"], u, NEAR_TIE_REL)
+    assert hard == 0 and near <= 2
+    chain = algo.get_chain_gpu().cpu().numpy()            # (B, T+1, d)
+    lps = algo.get_log_densities_gpu().cpu().numpy()
+    for c in range(B):
+        n = int(until[c])
+        np.testing.assert_array_equal(chain[c, : n + 1], ora["chain"][: n + 1, c])
+        _close_logp(lps[c, : n + 1], ora["logp"][: n + 1, c])
+    ok = until == T
+    np.testing.assert_array_equal(algo._batch.accept_count.cpu().numpy()[ok], ora["accept_count"][ok])
+    np.testing.assert_allclose(algo.esjd_per_chain().cpu().numpy()[ok], ora["esjd"][ok], rtol=2e-5, atol=1e-12)
+    np.testing.assert_allclose((algo._batch.sq_jump_sum.cpu().numpy() / (T - burn))[ok], ora["esjd"][ok], rtol=2e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("swap_mode", ["reference", "exchange"])
+@pytest.mark.parametrize("case", [("rough_carpet_d20", 20, 8, 0), ("rough_carpet_d20", 20, 5, 2), ("three_mixture_d10", 10, 3, 0),
+                                  ("even_rosenbrock_d10", 10, 13, 1), ("neal_funnel_d10", 10, 40, 4)])
+def test_pt_batch_matches_oracle(case, swap_mode):
+    """12 ladders, ragged ladder sizes (K not a power of two, K*lanes > one warp), both swap semantics."""
+    key, d, K, lanes = case
+    dev = _cuda()
+    _, PT = _algs()
+    t = product_target(key)
+    spec = t.spec()
+    rs = np.random.RandomState(K * 1000 + d)
+    L, T, burn, se = 12, 120, 10, 4
+    betas = [float(b) for b in np.geomspace(1.0, 0.02, K)]
+    x0 = (rs.randn(L, 1, d) * 0.5).astype(np.float32).repeat(K, axis=1)
+    std = np.sqrt(np.asarray([np.float32(0.5 / b) for b in betas], np.float32))
+    if key == "even_rosenbrock_d10":
+        std = std * 0.1
+    inc = (rs.randn(T, L, K, d).astype(np.float32) * std[None, None, :, None]).astype(np.float32)
+    u = rs.rand(T, L, K).astype(np.float32)
+    R = sum(1 for s in range(1, T + 1) if s % se == 0 and s > burn)
+    su = rs.rand(R, L, K - 1).astype(np.float32)
+    algo = PT(d, 0.5, t, beta_ladder=betas, swap_every=se, burn_in=burn, device=dev, num_ladders=L, store="all",
+              math_mode="ieee", swap_mode=swap_mode, initial_states=x0, lanes_per_chain=lanes)
+    dec, sdec = algo.run_injected(inc.reshape(T, L * K, d), u.reshape(T, L * K), su)
+    dec, sdec = dec.cpu().numpy().reshape(T, L, K), sdec.cpu().numpy()
+    ora = O.pt_run(spec, x0, betas, inc, u, su, se, burn_in=burn, swap_mode=swap_mode)
+    good = [l for l in range(L) if np.array_equal(dec[:, l], ora["decisions"][:, l]) and np.array_equal(sdec[:, l], ora["swap_decisions"][:, l])]
+    assert len(good) >= L - 1, "more than one ladder diverged (near ties should be rare)"
+    final = algo.current_states.cpu().numpy()
+    pair_acc = algo._batch.swap_accepts.cpu().numpy()
+    for l in good:
+        np.testing.assert_array_equal(final[l], ora["final_state"][l])
+        _close_logp(algo.current_log_densities.cpu().numpy()[l], ora["final_logp"][l])
+        np.testing.assert_array_equal(pair_acc[l, : K - 1], ora["pair_accepts"][l])
+        np.testing.assert_array_equal(algo._batch.accept_count.cpu().numpy().reshape(L, K)[l], ora["mh_accepts"][l])
+        np.testing.assert_allclose(algo._batch.sq_jump_sum.cpu().numpy().reshape(L, K)[l] / (T - burn), ora["esjd_per_temp"][l], rtol=2e-5, atol=1e-12)
+        assert int(algo._batch.swap_last_attempt.view(L, K)[l].max().item()) == int(ora["attempts_at_last_accept"][l])
+    all_chains = algo.get_all_chains_gpu()               # K tensors (L, T+1, d)
+    for l in good[:3]:
+        for k in (0, K - 1):
+            np.testing.assert_array_equal(all_chains[k][l].cpu().numpy(), ora["chain"][:, l, k])
+    assert algo.num_swap_attempts == R * (K - 1) * L
+
+
+def test_pt_laplace_uniform_extension_matches_oracle_composition():
+    """BASELINE config 4 shape (PT + Laplace / UniformRadius): no reference implementation exists; the oracle
+    composes the reference's proposal transforms with its PT step (parity unpinned by the reference)."""
+    dev = _cuda()
+    _, PT = _algs()
+    from rwm_pt_pytorch_b200.proposal_distributions import LaplaceProposal, UniformRadiusProposal
+    t = product_target("three_mixture_pm15_d50")
+    spec, d, K, L, T, se = t.spec(), 50, 8, 6, 60, 5
+    betas = O.geometric_ladder()
+    rs = np.random.RandomState(11)
+    x0 = np.zeros((L, K, d), np.float32)
+    u = rs.rand(T, L, K).astype(np.float32)
+    su = rs.rand(T // se, L, K - 1).astype(np.float32)
+    var_vec = np.full(d, 2.38 ** 2 / d, np.float32)
+    raw_u = rs.rand(T, L, K, d).astype(np.float32)
+    raw_z, raw_r = rs.randn(T, L, K, d).astype(np.float32), rs.rand(T, L, K).astype(np.float32)
+    for kind in ("laplace", "uniform"):
+        if kind == "laplace":
+            inc = np.stack([O.laplace_increments(raw_u[:, :, k].reshape(-1, d), var_vec, betas[k]).reshape(T, L, d) for k in range(K)], axis=2)
+            prop = LaplaceProposal(d, torch.tensor(var_vec), 1.0, torch.device("cpu"), torch.float32)
+        else:
+            inc = np.stack([O.uniform_radius_increments(raw_z[:, :, k].reshape(-1, d), raw_r[:, :, k].reshape(-1), 1.0, betas[k]).reshape(T, L, d) for k in range(K)], axis=2)
+            prop = UniformRadiusProposal(d, 1.0, 1.0, torch.device("cpu"), torch.float32)
+        algo = PT(d, None, t, beta_ladder=betas, swap_every=se, device=dev, num_ladders=L, store="cold", math_mode="ieee",
+                  proposal_distribution=prop, initial_states=x0)
+        dec, sdec = algo.run_injected(inc.reshape(T, L * K, d), u.reshape(T, L * K), su)
+        ora = O.pt_run(spec, x0, betas, inc, u, su, se)
+        good = [l for l in range(L) if np.array_equal(dec.cpu().numpy().reshape(T, L, K)[:, l], ora["decisions"][:, l])
+                and np.array_equal(sdec.cpu().numpy()[:, l], ora["swap_decisions"][:, l])]
+        assert len(good) >= L - 1
+        cold = algo.get_cold_chain_gpu().cpu().numpy()      # (L, T+1, d)
+        for l in good:
+            np.testing.assert_array_equal(cold[l], ora["chain"][:, l, 0])
+
+
+# ---- native Philox stream: statistical agreement --------------------------------------------------------
+def _se_of_rate(p, n_eff):
+    return np.sqrt(max(p * (1 - p), 1e-6) / n_eff)
+
+
+@pytest.mark.parametrize("key,d,x,acc_ref,acc_se,esjd_ref,esjd_se", [
+    # seed-averaged curves of the reference's data/ (BASELINE.md section 2): EvenRosenbrock, variance x^2/d, burn-in 1000
+    ("even_rosenbrock_d20", 20, 0.297436, 0.18487, 0.00610, 0.014801, 0.000514),
+    ("even_rosenbrock_d10", 10, 0.161282, 0.45916, 0.01148, 0.010940, 0.000302),
+    ("even_rosenbrock_d30", 30, 0.085641, 0.71921, 0.00227, 0.005212, 0.000017),
+])
+def test_native_rng_matches_reference_statistics(key, d, x, acc_ref, acc_se, esjd_ref, esjd_se):
+    """256 chains x 1e6 steps (the reference's own run length) against the reference's recorded runs; its s.e. over
+    ~25 seed files is the dominant uncertainty."""
+    dev = _cuda()
+    RWM, _ = _algs()
+    t = product_target(key)
+    np.random.seed(7)
+    algo = RWM(d, x * x / d, t, burn_in=1000, device=dev, num_chains=256, seed=12345)
+    algo.generate_samples(1_000_000)
+    acc = algo.acceptance_rates.cpu().numpy()
+    esjd = algo.esjd_per_chain().cpu().numpy()
+    acc_mean, esjd_mean = acc.mean(), esjd.mean()
+    acc_err = np.hypot(acc.std(ddof=1) / np.sqrt(len(acc)), acc_se)
+    esjd_err = np.hypot(esjd.std(ddof=1) / np.sqrt(len(esjd)), esjd_se)
+    assert abs(acc_mean - acc_ref) <= 3 * acc_err, (acc_mean, acc_ref, acc_err)
+    assert abs(esjd_mean - esjd_ref) <= 3 * esjd_err + 0.02 * esjd_ref, (esjd_mean, esjd_ref, esjd_err)
+
+
+@pytest.mark.parametrize("key,d,var,prop", [("rough_carpet_pm4_d20", 20, 1.929231 ** 2 / 20, "normal"),
+                                            ("mvn_identity_d50", 50, 2.38 ** 2 / 50, "laplace"),
+                                            ("mvn_identity_d50", 50, 2.0, "uniform"),
+                                            ("neal_funnel_d10", 10, 0.5, "normal"),
+                                            ("iid_gamma_d8", 8, 2.0, "normal")])
+def test_native_rng_matches_oracle_statistics(key, d, var, prop):
+    """Same configuration run by the kernel (Philox, fast math) and by the oracle (NumPy randomness, the reference's
+    proposal transforms): acceptance within 3 standard errors, ESJD within 2 % (+ 3 s.e.)."""
+    dev = _cuda()
+    RWM, _ = _algs()
+    from rwm_pt_pytorch_b200.proposal_distributions import LaplaceProposal, UniformRadiusProposal
+    t = product_target(key)
+    spec = t.spec()
+    B_o, T, burn = 96, 1500, 300
+    rs = np.random.RandomState(5)
+    x0 = np.stack([O.initial_state(t.get_name(), d, rs) for _ in range(B_o)]).astype(np.float32)
+    if prop == "normal":
+        inc = O.normal_increments(rs.randn(T, B_o, d), var, 1.0)
+        kw = dict(var=var)
+    elif prop == "laplace":
+        inc = O.laplace_increments(rs.rand(T * B_o, d), np.full(d, var, np.float32), 1.0).reshape(T, B_o, d)
+        kw = dict(var=None, proposal_distribution=LaplaceProposal(d, torch.full((d,), var), 1.0, torch.device("cpu"), torch.float32))
+    else:
+        inc = O.uniform_radius_increments(rs.randn(T * B_o, d), rs.rand(T * B_o), var, 1.0).reshape(T, B_o, d)
+        kw = dict(var=None, proposal_distribution=UniformRadiusProposal(d, var, 1.0, torch.device("cpu"), torch.float32))
+    ora = O.rwm_run(spec, x0, 1.0, inc, rs.rand(T, B_o), burn_in=burn, keep_states=False)
+    B = 2048
+    np.random.seed(3)
+    algo = RWM(d, target_dist=t, burn_in=burn, device=dev, num_chains=B, seed=99, **kw)
+    algo.generate_samples(T - burn)
+    acc_g, esjd_g = algo.acceptance_rates.cpu().numpy(), algo.esjd_per_chain().cpu().numpy()
+    acc_o, esjd_o = ora["acceptance_rate"], ora["esjd"]
+    acc_err = np.hypot(acc_g.std(ddof=1) / np.sqrt(B), acc_o.std(ddof=1) / np.sqrt(B_o))
+    esjd_err = np.hypot(esjd_g.std(ddof=1) / np.sqrt(B), esjd_o.std(ddof=1) / np.sqrt(B_o))
+    assert abs(acc_g.mean() - acc_o.mean()) <= 3 * acc_err, (acc_g.mean(), acc_o.mean(), acc_err)
+    assert abs(esjd_g.mean() - esjd_o.mean()) <= 3 * esjd_err + 0.02 * esjd_o.mean(), (esjd_g.mean(), esjd_o.mean(), esjd_err)
+
+
+def test_pt_native_rng_statistics_vs_oracle():
+    """README configuration of the reference (RoughCarpet d=20, var 0.9, geometric ladder, swap_every 10,
+    burn-in 2000): swap acceptance and cold-chain ESJD from the kernel's own Philox stream against the oracle with
+    NumPy randomness, and against the reference's recorded run (swap 0.2795)."""
+    dev = _cuda()
+    _, PT = _algs()
+    t = product_target("rough_carpet_d20")
+    spec, d = t.spec(), 20
+    betas = O.geometric_ladder()
+    K, L_o, T, burn, se = 8, 24, 6000, 2000, 10
+    rs = np.random.RandomState(8)
+    std = np.sqrt(np.asarray([np.float32(0.9 / b) for b in betas], np.float32))
+    inc = (rs.randn(T, L_o, K, d).astype(np.float32) * std[None, None, :, None]).astype(np.float32)
+    R = sum(1 for s in range(1, T + 1) if s % se == 0 and s > burn)
+    ora = O.pt_run(spec, np.zeros((L_o, K, d), np.float32), betas, inc, rs.rand(T, L_o, K), rs.rand(R, L_o, K - 1), se,
+                   burn_in=burn, keep_states=False)
+    L = 1024
+    algo = PT(d, 0.9, t, geom_temp_spacing=True, swap_every=se, burn_in=burn, device=dev, num_ladders=L, seed=2024)
+    algo.generate_samples(T - burn)
+    rate_g = algo.swap_acceptance_rates
+    rate_o = ora["swap_accepts"] / ora["swap_attempts"]
+    err = np.hypot(rate_g.std(ddof=1) / np.sqrt(L), rate_o.std(ddof=1) / np.sqrt(L_o))
+    assert abs(rate_g.mean() - rate_o.mean()) <= 3 * err, (rate_g.mean(), rate_o.mean(), err)
+    assert abs(rate_g.mean() - 0.2795) < 0.02
+    e_g, e_o = algo.esjd_per_ladder().cpu().numpy(), ora["cold_esjd"]
+    e_err = np.hypot(e_g.std(ddof=1) / np.sqrt(L), e_o.std(ddof=1) / np.sqrt(L_o))
+    assert abs(e_g.mean() - e_o.mean()) <= 3 * e_err + 0.02 * e_o.mean(), (e_g.mean(), e_o.mean(), e_err)
+    mh_g = algo.mh_acceptance_rates.cpu().numpy().mean(axis=0)
+    mh_o = ora["mh_accepts"].mean(axis=0) / (T - burn)
+    np.testing.assert_allclose(mh_g, mh_o, atol=0.02)
+
+
+# ---- proposal plugins, swap kernel, ESJD kernel -----------------------------------------------------------
+def test_proposal_plugin_samplers_moments():
+    dev = _cuda()
+    from rwm_pt_pytorch_b200.proposal_distributions import NormalProposal, LaplaceProposal, UniformRadiusProposal
+    n, d = 200_000, 10
+    torch.manual_seed(0)
+    p = NormalProposal(d, 0.37, 0.25, dev, torch.float32)
+    s = p.sample(n)
+    assert s.shape == (n, d) and s.device.type == "cuda"
+    assert abs(s.mean().item()) < 0.01 and abs(s.var().item() - 0.37 / 0.25) < 0.02
+    assert abs((s ** 4).mean().item() / s.var().item() ** 2 - 3.0) < 0.1          # Gaussian kurtosis
+    s2 = p.sample(n)
+    assert not torch.equal(s, s2)                                                 # the stream advances
+    var_vec = torch.linspace(0.05, 1.3, d)
+    s = LaplaceProposal(d, var_vec, 0.5, dev, torch.float32).sample(n)
+    np.testing.assert_allclose(s.var(dim=0).cpu().numpy(), (var_vec / 0.5).numpy(), rtol=0.03)
+    assert abs((s[:, 3] ** 4).mean().item() / s[:, 3].var().item() ** 2 - 6.0) < 0.4   # Laplace kurtosis
+    s = UniformRadiusProposal(d, 1.7, 0.25, dev, torch.float32).sample(n)
+    r = s.norm(dim=1)
+    R = 1.7 / 0.5
+    assert r.max().item() <= R * (1 + 1e-5)
+    assert abs((r ** 2).mean().item() - R * R * d / (d + 2)) < 0.02 * R * R
+    assert abs(s.mean().item()) < 0.01
+
+
+@pytest.mark.parametrize("swap_mode", ["reference", "exchange"])
+def test_standalone_swap_kernel_matches_oracle(swap_mode):
+    import ctypes as C
+    from rwm_pt_pytorch_b200 import _lib
+    dev = _cuda()
+    lib = _lib.load()
+    rs = np.random.RandomState(4)
+    L, K, d = 37, 11, 23
+    betas = np.geomspace(1.0, 0.05, K).astype(np.float32)
+    x = rs.randn(L, K, d).astype(np.float32)
+    lp = (-0.5 * (x ** 2).sum(-1) * rs.uniform(0.5, 2.0, (L, K))).astype(np.float32)
+    su = rs.rand(L, K - 1).astype(np.float32)
+    # oracle sweep, starting from the given logp (zero increments + always-reject uniforms keep the MH step inert)
+    xs, lps = x.copy(), lp.copy()
+    want_dec = np.zeros((L, K - 1), np.uint8)
+    for j in range(K - 1):
+        lsp = O.swap_log_prob(betas[j], betas[j + 1], lps[:, j], lps[:, j + 1])
+        ok = su[:, j] < np.minimum(np.float32(1), np.exp(lsp))
+        want_dec[:, j] = ok
+        if swap_mode == "reference":
+            xs[ok, j] = xs[ok, j + 1]; lps[ok, j] = lps[ok, j + 1]
+        else:
+            tmp = xs[ok, j].copy(); xs[ok, j] = xs[ok, j + 1]; xs[ok, j + 1] = tmp
+            tl = lps[ok, j].copy(); lps[ok, j] = lps[ok, j + 1]; lps[ok, j + 1] = tl
+    xd, lpd = torch.tensor(x, device=dev), torch.tensor(lp, device=dev)
+    bd = torch.tensor(np.tile(betas, L), device=dev)
+    sud = torch.tensor(su, device=dev)
+    dec = torch.zeros((L, K - 1), device=dev, dtype=torch.uint8)
+    acc = torch.zeros((L, K - 1), device=dev, dtype=torch.int64)
+    _lib.check(lib.rwmpt_pt_swap(xd.data_ptr(), lpd.data_ptr(), bd.data_ptr(), L, K, d, _lib.SWAP_MODES[swap_mode],
+                                 sud.data_ptr(), 0, 0, 0, dec.data_ptr(), acc.data_ptr(), _lib.stream_ptr(dev)))
+    np.testing.assert_array_equal(dec.cpu().numpy(), want_dec)
+    np.testing.assert_array_equal(xd.cpu().numpy(), xs)
+    np.testing.assert_array_equal(lpd.cpu().numpy(), lps)
+    np.testing.assert_array_equal(acc.cpu().numpy(), want_dec.astype(np.int64))
+
+
+def test_esjd_reduction_kernel():
+    import ctypes as C
+    from rwm_pt_pytorch_b200 import _lib
+    dev = _cuda()
+    lib = _lib.load()
+    rs = np.random.RandomState(2)
+    for (B, S, d, first, n) in [(5, 400, 20, 30, 370), (1, 1001, 50, 0, 1001), (64, 33, 3, 2, 31), (3, 10, 7, 4, 1)]:
+        x = np.cumsum(rs.randn(B, S, d) * (rs.rand(B, S, 1) < 0.4), axis=1).astype(np.float32)
+        xd = torch.tensor(x, device=dev)
+        out = torch.empty(B, device=dev, dtype=torch.float64)
+        moved = torch.empty(B, device=dev, dtype=torch.int64)
+        _lib.check(lib.rwmpt_esjd_reduce(xd.data_ptr(), B, S, first, n, d, out.data_ptr(), moved.data_ptr(), _lib.stream_ptr(dev)))
+        seg = x[:, first:first + n].astype(np.float64)
+        if n >= 2:
+            sq = ((seg[:, 1:] - seg[:, :-1]) ** 2).sum(-1)
+            np.testing.assert_allclose(out.cpu().numpy(), sq.mean(axis=1), rtol=1e-6)
+            np.testing.assert_array_equal(moved.cpu().numpy(), (sq != 0).sum(axis=1))
+            assert O.esjd_from_chain(x[0, :first + n], first) == pytest.approx(out[0].item(), rel=1e-5)
+        else:
+            assert (out == 0).all()
+
+
+# ---- edge cases, resumability, sharding invariance, host-buffer entry --------------------------------------
+def test_empty_and_invalid_inputs():
+    import ctypes as C
+    from rwm_pt_pytorch_b200 import _lib
+    dev = _cuda()
+    RWM, PT = _algs()
+    t = product_target("even_rosenbrock_d10")
+    algo = RWM(10, 0.01, t, device=dev, num_chains=3, store="none")
+    out = algo.generate_samples(0)                      # zero steps: nothing happens, nothing breaks
+    assert out.shape == (3, 0, 10) and algo.total_steps == 0
+    with pytest.raises(ValueError):
+        RWM(10, 0.01, t, device=dev, lanes_per_chain=3).generate_samples(5)
+    from rwm_pt_pytorch_b200.target_distributions import EvenRosenbrockTorch
+    big = EvenRosenbrockTorch(500, device="cpu")         # 500 coordinates > 13 per lane x 32 lanes
+    with pytest.raises(NotImplementedError):
+        RWM(500, 0.01, big, device=dev).generate_samples(5)
+    lib = _lib.load()
+    tgt = _lib.target_struct(t.family_id, 10, t.device_params(dev))
+    assert lib.rwmpt_log_density(tgt, None, 0, None, 0, None) == 0                 # n = 0
+    with pytest.raises(ValueError):
+        _lib.check(lib.rwmpt_log_density(tgt, None, 4, None, 0, None))
+    with pytest.raises(ValueError):
+        t.log_density(torch.zeros(3, 7, device=dev))
+
+
+def test_hypercube_chain_starting_outside_support_recovers():
+    """-inf current density & finite proposal -> lar = +inf -> accept (NaN/inf semantics)."""
+    dev = _cuda()
+    RWM, _ = _algs()
+    t = product_target("hypercube_01_d4")
+    x0 = np.full((8, 4), -0.05, np.float32)
+    algo = RWM(4, 0.02, t, device=dev, num_chains=8, store="all", initial_states=x0, seed=1)
+    assert torch.isinf(t.log_density(torch.tensor(x0))).all()
+    algo.generate_samples(4000)
+    lp = algo.get_log_densities_gpu()
+    assert torch.isinf(lp[:, 0]).all() and torch.isfinite(lp[:, -1]).all()
+    inside = (algo.current_state >= 0).all(dim=1) & (algo.current_state <= 1).all(dim=1)
+    assert inside.all()
+    first_in = (torch.isfinite(lp)).float().argmax(dim=1)
+    for c in range(8):                                   # once inside, never leaves
+        assert torch.isfinite(lp[c, int(first_in[c]):]).all()
+
+
+def test_resume_equals_single_run_and_sharding_is_invariant():
+    dev = _cuda()
+    RWM, PT = _algs()
+    t = product_target("rough_carpet_d20")
+    x0 = np.random.RandomState(0).randn(64, 20).astype(np.float32)
+    one = RWM(20, 0.4, t, burn_in=50, device=dev, num_chains=64, store="none", seed=77, initial_states=x0)
+    one.generate_samples(350)
+    two = RWM(20, 0.4, t, burn_in=50, device=dev, num_chains=64, store="none", seed=77, initial_states=x0)
+    two._ensure_batch(1)
+    two._batch.run(123); two._batch.run(277); two._refresh_stats()
+    assert torch.equal(one.current_state, two.current_state)
+    assert torch.equal(one._batch.accept_count, two._batch.accept_count)
+    torch.testing.assert_close(one._batch.sq_jump_sum, two._batch.sq_jump_sum, rtol=1e-6, atol=0)
+    # two "ranks" of 32 chains each, Philox subsequence = global chain id
+    a = RWM(20, 0.4, t, burn_in=50, device=dev, num_chains=32, store="none", seed=77, initial_states=x0[:32], chain_id_base=0)
+    b = RWM(20, 0.4, t, burn_in=50, device=dev, num_chains=32, store="none", seed=77, initial_states=x0[32:], chain_id_base=32)
+    a.generate_samples(350); b.generate_samples(350)
+    assert torch.equal(torch.cat([a.current_state, b.current_state]), one.current_state)
+    # PT: ladders are the sharded unit
+    kw = dict(geom_temp_spacing=True, swap_every=10, burn_in=20, device=dev, store="none", seed=5)
+    full = PT(20, 0.9, t, num_ladders=8, **kw); full.generate_samples(300)
+    h1 = PT(20, 0.9, t, num_ladders=4, chain_id_base=0, **kw); h1.generate_samples(300)
+    h2 = PT(20, 0.9, t, num_ladders=4, chain_id_base=4 * 8, **kw); h2.generate_samples(300)
+    assert torch.equal(torch.cat([h1.current_states, h2.current_states]), full.current_states)
+    assert full.num_swap_acceptances == h1.num_swap_acceptances + h2.num_swap_acceptances
+
+
+def test_step_api_and_reference_bookkeeping():
+    """step() one at a time equals one generate_samples launch; reference attribute semantics hold."""
+    dev = _cuda()
+    RWM, PT = _algs()
+    t = product_target("even_rosenbrock_d10")
+    a = RWM(10, 0.01, t, burn_in=5, device=dev, pre_allocate_steps=40, seed=3)
+    assert a.current_state is None and a.chain_index == 0
+    s = a.generate_samples(40)
+    assert s.shape == (40, 10) and a.chain_index == 46 and a.total_steps == 45
+    assert a.get_chain_gpu().shape == (46, 10) and a.pre_allocated_chain.shape == (46, 10)
+    assert a.acceptance_rate == a.num_acceptances / 40
+    b = RWM(10, 0.01, t, burn_in=5, device=dev, pre_allocate_steps=40, seed=3, initial_states=a._x0)
+    for _ in range(45):
+        b.step()
+    assert torch.equal(b.get_chain_gpu(), a.get_chain_gpu()) and b.num_acceptances == a.num_acceptances
+    a.reset()
+    assert a.total_steps == 0 and a.current_state is None
+    p = PT(10, 0.01, t, beta_ladder=[1.0, 0.5, 0.1], swap_every=4, burn_in=8, device=dev, pre_allocate_steps=60, seed=9)
+    cold = p.generate_samples(60)
+    assert cold.shape == (60, 10) and p.step_counter == 68 and len(p.chain) == 69
+    assert len(p.get_all_chains_gpu()) == 3 and p.get_all_chains_gpu()[2].shape == (69, 10)
+    assert p.num_swap_attempts == 2 * sum(1 for s in range(1, 69) if s % 4 == 0 and s > 8)
+    q = PT(10, 0.01, t, beta_ladder=[1.0, 0.5, 0.1], swap_every=4, burn_in=8, device=dev, pre_allocate_steps=60, seed=9,
+           initial_states=p._x0_full)
+    for _ in range(68):
+        q.step()
+    assert torch.equal(q.get_cold_chain_gpu(), p.get_cold_chain_gpu())
+    assert q.num_swap_acceptances == p.num_swap_acceptances and q.swap_acceptance_rate == p.swap_acceptance_rate
+
+
+def test_simulation_harness_end_to_end():
+    dev = _cuda()
+    RWM, PT = _algs()
+    from rwm_pt_pytorch_b200.interfaces import MCMCSimulation_GPU
+    t = product_target("mvn_identity_d50")
+    np.random.seed(0)   # the initial state is drawn from NumPy's global RNG before the harness seeds it
+    sim = MCMCSimulation_GPU(50, proposal_config={'name': 'Laplace', 'params': {'base_variance_vector': 2.38 ** 2 / 50}},
+                             num_iterations=20000, algorithm=RWM, target_dist=t, seed=42, burn_in=1000, device="cuda")
+    chain = sim.generate_samples()
+    assert isinstance(chain, list) and len(chain) == 20000 and len(chain[0]) == 50
+    assert 0.15 < sim.acceptance_rate() < 0.40 and sim.expected_squared_jump_distance() > 0
+    with pytest.raises(ValueError, match="reset"):
+        sim.generate_samples()
+    np.random.seed(0)
+    sim2 = MCMCSimulation_GPU(50, proposal_config={'name': 'Laplace', 'params': {'base_variance_vector': 2.38 ** 2 / 50}},
+                              num_iterations=20000, algorithm=RWM, target_dist=t, seed=42, burn_in=1000, device="cuda")
+    assert sim2.generate_samples() == chain                       # `seed` really seeds the run
+    simp = MCMCSimulation_GPU(20, sigma=0.9, num_iterations=5000, algorithm=PT, target_dist=product_target("rough_carpet_d20"),
+                              seed=1, burn_in=500, device="cuda", swap_every=10, geom_temp_spacing=True)
+    simp.generate_samples(as_list=False)
+    assert 0.15 < simp.algorithm.swap_acceptance_rate < 0.45 and simp.pt_expected_squared_jump_distance() > 0
+
+
+def test_host_buffer_entry_matches_device_path():
+    import ctypes as C
+    from rwm_pt_pytorch_b200 import _lib
+    dev = _cuda()
+    _, PT = _algs()
+    t = product_target("rough_carpet_d20")
+    L, K, d, T = 16, 8, 20, 200
+    algo = PT(d, 0.9, t, geom_temp_spacing=True, swap_every=10, burn_in=20, device=dev, num_ladders=L, store="none", seed=31)
+    lp0 = algo.current_log_densities.cpu().numpy().reshape(-1).copy()
+    algo.generate_samples(T - 20)
+    lib = _lib.load()
+    params = t.pack().numpy().copy()
+    state = np.zeros((L * K, d), np.float32)
+    logp = lp0.copy()
+    beta = np.tile(np.asarray(algo.beta_ladder, np.float32), L)
+    scale = np.tile(algo._scales, L)
+    acc = np.zeros(L * K, np.uint64); sq = np.zeros(L * K, np.float64)
+    sacc = np.zeros((L, K - 1), np.uint64); last = np.zeros(L * K, np.uint64)
+    a = _lib.RunArgs()
+    a.target = _lib.TargetT(t.family_id, d, params.ctypes.data, params.size)
+    a.proposal_family, a.n_temps = 0, K
+    a.prop_scale, a.beta = scale.ctypes.data, beta.ctypes.data
+    a.n_ladders, a.n_steps, a.burn_in, a.step_offset = L, T, 20, 0
+    a.swap_every, a.swap_mode = 10, 0
+    a.state, a.logp = state.ctypes.data, logp.ctypes.data
+    a.seed = 31
+    a.accept_count, a.sq_jump_sum = acc.ctypes.data, sq.ctypes.data
+    a.swap_accepts, a.swap_last_attempt = sacc.ctypes.data, last.ctypes.data
+    h2d, d2h = C.c_uint64(), C.c_uint64()
+    _lib.check(lib.rwmpt_run_host(C.byref(a), 0, C.byref(h2d), C.byref(d2h)))
+    np.testing.assert_array_equal(state, algo._batch.state.cpu().numpy())
+    np.testing.assert_array_equal(acc.astype(np.int64), algo._batch.accept_count.cpu().numpy())
+    np.testing.assert_array_equal(sacc.astype(np.int64), algo._batch.swap_accepts.cpu().numpy())
+    assert h2d.value > 0 and d2h.value >= state.nbytes
+
+
+def test_iterative_ladder_construction_runs_on_gpu_densities():
+    dev = _cuda()
+    _, PT = _algs()
+    from rwm_pt_pytorch_b200.target_distributions import RoughCarpetDistributionTorch
+    torch.manual_seed(0)
+    t = RoughCarpetDistributionTorch(5, device=dev, mode_centers=[-4.0, 0.0, 4.0])
+    p = PT(5, 2.38 ** 2 / 5, t, iterative_temp_spacing=True, swap_acceptance_rate=0.3, N_samples_swap_est=20000,
+           iterative_tolerance=0.02, swap_every=5, burn_in=100, device=dev, seed=4)
+    lad = p.beta_ladder
+    assert lad[0] == 1.0 and abs(lad[-1] - 0.01) < 1e-9 and all(a > b for a, b in zip(lad, lad[1:])) and len(lad) >= 3
+    assert p.get_name() == "PT_RWM_GPU_ULTRA_FUSED_ITERATIVE_LADDER"
+    p.generate_samples(3000)
+    assert 0.1 < p.swap_acceptance_rate < 0.6
