@@ -172,6 +172,9 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   }
   if (r->lanes_per_chain < 0 || r->lanes_per_chain > 32 || (r->lanes_per_chain & (r->lanes_per_chain - 1)))
     return fail(RWMPT_EINVAL, "lanes_per_chain must be 0 or a power of two <= 32");
+  const bool test_mode = inject || r->inj_swap_uniforms || r->decisions || r->swap_decisions;
+  if (test_mode && r->math_mode != RWMPT_MATH_IEEE)
+    return fail(RWMPT_ENOTSUP, "injected randomness / decision outputs (test mode) need math_mode = RWMPT_MATH_IEEE");
   if (r->n_ladders == 0 || r->n_steps == 0) return RWMPT_OK;  // empty input: nothing to do
 
   LaunchGeom g;
@@ -270,8 +273,6 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(float* __restrict__ state,
   float* s_b = sm + K;            // [K]
   int* s_src = (int*)(sm + 2 * K);  // [K]
   float* s_x = sm + 3 * K;        // [K, d]
-  KernelArgs ka;  // only the key fields are used by swap_uniform
-  ka.key0 = k0; ka.key1 = k1;
   for (long long l = blockIdx.x; l < n_ladders; l += gridDim.x) {
     const long long c0 = l * K;
     for (int i = threadIdx.x; i < K * d; i += blockDim.x) s_x[i] = state[c0 * d + i];
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(float* __restrict__ state,
     if (threadIdx.x == 0) {
       const unsigned long long lg = (unsigned long long)(ladder_base + l);
       for (int j = 0; j < K - 1; ++j) {
-        const float u = su ? su[l * (K - 1) + j] : swap_uniform(ka, lg, (unsigned long long)round_index, j);
+        const float u = su ? su[l * (K - 1) + j] : swap_uniform(k0, k1, lg, (unsigned long long)round_index, j);
         bool ok;
         if (swap_mode == RWMPT_SWAP_REFERENCE) {
           // slot j+1 still holds its pre-sweep occupant when pair j is examined

@@ -146,26 +146,41 @@ struct Mth<false> {
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ float group_sum(float v, int W) {
-  if (W > 16) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 16));
-  if (W > 8) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 8));
-  if (W > 4) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 4));
-  if (W > 2) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 2));
-  if (W > 1) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 1));
+// WT > 0: lanes-per-chain known at compile time (fully unrolled butterfly); WT == 0: runtime W.
+template <int WT>
+__device__ __forceinline__ float group_sum_w(float v, int W) {
+  if constexpr (WT > 0) {
+#pragma unroll
+    for (int o = WT / 2; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, o));
+  } else {
+    if (W > 16) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 16));
+    if (W > 8) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 8));
+    if (W > 4) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 4));
+    if (W > 2) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 2));
+    if (W > 1) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 1));
+  }
   return v;
 }
 
-__device__ __forceinline__ double group_sum_f64(double v, int W) {
-  if (W > 16) v += __shfl_xor_sync(kFull, v, 16);
-  if (W > 8) v += __shfl_xor_sync(kFull, v, 8);
-  if (W > 4) v += __shfl_xor_sync(kFull, v, 4);
-  if (W > 2) v += __shfl_xor_sync(kFull, v, 2);
-  if (W > 1) v += __shfl_xor_sync(kFull, v, 1);
+template <int WT>
+__device__ __forceinline__ double group_sum_f64_w(double v, int W) {
+  if constexpr (WT > 0) {
+#pragma unroll
+    for (int o = WT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  } else {
+    if (W > 16) v += __shfl_xor_sync(kFull, v, 16);
+    if (W > 8) v += __shfl_xor_sync(kFull, v, 8);
+    if (W > 4) v += __shfl_xor_sync(kFull, v, 4);
+    if (W > 2) v += __shfl_xor_sync(kFull, v, 2);
+    if (W > 1) v += __shfl_xor_sync(kFull, v, 1);
+  }
   return v;
 }
 
 // Per-thread view of where it sits inside its chain.
-struct Ctx {
+template <int WT_>
+struct CtxT {
+  static constexpr int WT = WT_;
   const float* P;  // target params
   int d;           // dimension
   int W;           // lanes per chain
@@ -174,10 +189,15 @@ struct Ctx {
   int lane;        // lane in warp
   int leader;      // lane (in warp) of sub == 0 of this chain
 };
+using Ctx = CtxT<0>;
+
+template <class C>
+__device__ __forceinline__ float group_sum(float v, const C& c) { return group_sum_w<C::WT>(v, c.W); }
 
 // value of `v` held by lane `sub+delta` of the same chain (garbage at the group edge: callers mask it)
 __device__ __forceinline__ float from_next_lane(float v) { return __shfl_down_sync(kFull, v, 1); }
 __device__ __forceinline__ float from_prev_lane(float v) { return __shfl_up_sync(kFull, v, 1); }
-__device__ __forceinline__ float from_leader(float v, const Ctx& c) { return __shfl_sync(kFull, v, c.leader); }
+template <class C>
+__device__ __forceinline__ float from_leader(float v, const C& c) { return __shfl_sync(kFull, v, c.leader); }
 
 }  // namespace rwmpt

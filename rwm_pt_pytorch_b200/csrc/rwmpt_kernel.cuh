@@ -43,12 +43,14 @@ __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, 
 __host__ __device__ constexpr int philox_calls_per_step(int E) { return (E + 2 + 3) / 4; }
 
 // Raw per-step randomness of one lane: E standard normals or E uniforms, plus the chain's accept uniform
-// and (UniformRadius) radius uniform, both taken from the leader lane.
-template <int E, bool IEEE>
-__device__ __forceinline__ void draw_increments(const KernelArgs& a, const Ctx& c, float (&inc)[E], float& u_acc,
+// and (UniformRadius) radius uniform, both taken from the leader lane.  PF >= 0: proposal family known at
+// compile time (no per-step branch); PF < 0: runtime switch on a.prop_family.
+template <int E, bool IEEE, int PF, class C>
+__device__ __forceinline__ void draw_increments(const KernelArgs& a, const C& c, float (&inc)[E], float& u_acc,
                                                 unsigned long long s, unsigned long long chain_gid, float scale,
                                                 const float (&dscale)[E]) {
   constexpr int NC = philox_calls_per_step(E);
+  const int pf = PF >= 0 ? PF : a.prop_family;
   uint32_t w[4 * NC];
   const uint32_t c0 = (uint32_t)s;
   const uint32_t c1hi = ((uint32_t)(s >> 32) << 16) | ((uint32_t)c.sub << 8);
@@ -58,7 +60,7 @@ __device__ __forceinline__ void draw_increments(const KernelArgs& a, const Ctx& 
     w[4 * k + 0] = r.x; w[4 * k + 1] = r.y; w[4 * k + 2] = r.z; w[4 * k + 3] = r.w;
   }
   u_acc = from_leader(u01_from_bits(w[4 * NC - 1]), c);
-  if (a.prop_family == RWMPT_P_LAPLACE) {
+  if (pf == RWMPT_P_LAPLACE) {
     // laplace.py:47-69: u in (-.5,.5); -s * sign(u) * log1p(max(-2|u|, -0.999999))
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -73,7 +75,7 @@ __device__ __forceinline__ void draw_increments(const KernelArgs& a, const Ctx& 
   float z[E + 1];
 #pragma unroll
   for (int p = 0; p < (E + 1) / 2; ++p) box_muller<IEEE>(w[2 * p], w[2 * p + 1], z[2 * p], z[2 * p + 1]);
-  if (a.prop_family == RWMPT_P_NORMAL) {
+  if (pf == RWMPT_P_NORMAL) {
     // normal.py:47-55: randn * std
 #pragma unroll
     for (int e = 0; e < E; ++e) inc[e] = z[e] * scale;
@@ -83,7 +85,7 @@ __device__ __forceinline__ void draw_increments(const KernelArgs& a, const Ctx& 
 #pragma unroll
     for (int e = 0; e < E; ++e)
       if (c.base + e < c.d) n2 = fmaf(z[e], z[e], n2);
-    n2 = group_sum(n2, c.W);
+    n2 = group_sum(n2, c);
     const float nrm = IEEE ? sqrtf(n2) : sqrt_approx(n2);
     const float safe = nrm > 1e-12f ? nrm : 1.0f;
     const float ur = from_leader(u01_from_bits(w[4 * NC - 2]), c);
@@ -96,11 +98,10 @@ __device__ __forceinline__ void draw_increments(const KernelArgs& a, const Ctx& 
 }
 
 // One uniform per (ladder, sweep, pair) on a separate Philox key.
-__device__ __forceinline__ float swap_uniform(const KernelArgs& a, unsigned long long ladder_gid, unsigned long long round,
-                                              int pair) {
+__device__ __forceinline__ float swap_uniform(unsigned key0, unsigned key1, unsigned long long ladder_gid,
+                                              unsigned long long round, int pair) {
   const uint4 r = philox4x32_10((uint32_t)round, ((uint32_t)(round >> 32) & 0xffffu) | ((uint32_t)(pair >> 2) << 16),
-                                (uint32_t)ladder_gid, (uint32_t)(ladder_gid >> 32), a.key0 ^ 0x5851F42Du,
-                                a.key1 ^ 0x4C957F2Du);
+                                (uint32_t)ladder_gid, (uint32_t)(ladder_gid >> 32), key0 ^ 0x5851F42Du, key1 ^ 0x4C957F2Du);
   const int q = pair & 3;
   const uint32_t w = q == 0 ? r.x : (q == 1 ? r.y : (q == 2 ? r.z : r.w));
   return u01_from_bits(w);
@@ -115,14 +116,17 @@ __device__ __forceinline__ bool swap_accept(float bj, float bk, float lj, float 
   return u < p;  // NaN -> false
 }
 
-template <template <int, bool> class Target, int E, bool IEEE>
+// Template parameters: Target functor; E coordinates per lane; IEEE parity arithmetic; WT lanes per chain (0 = runtime);
+// PF proposal family (-1 = runtime); TEST = injected randomness / decision outputs available (not software-pipelined).
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool TEST>
 __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a) {
   using M = Mth<IEEE>;
   extern __shared__ float smem[];
 
-  const int W = a.W, K = a.K, d = a.dim;
+  const int W = WT > 0 ? WT : a.W;
+  const int K = a.K, d = a.dim;
   const int cl = threadIdx.x / W;  // chain within CTA
-  Ctx c;
+  CtxT<WT> c;
   c.P = a.P; c.d = d; c.W = W;
   c.sub = threadIdx.x % W;
   c.base = c.sub * E;
@@ -181,17 +185,24 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     store_m = (nxt - a.store_start) / a.thin - 1;
   }
   const long long store_chain = a.store_mode == RWMPT_STORE_ALL ? chain : ladder;
+  const long long burn_t = a.burn_in > a.step_offset ? a.burn_in - a.step_offset : 0;  // local steps t >= burn_t count
 
   unsigned long long n_acc = 0, n_swap_acc = 0, last_attempt = 0;
   long long round_local = 0;
   float jump_f = 0.0f;
   double jump_d = 0.0;
 
+  // software pipeline: the increments of step t+1 are drawn while step t's density / reduction / accept chain
+  // is in flight (they do not depend on the state), which doubles the independent work a warp can issue.
+  float inc[E], u = 0.0f;
+  const bool inject = TEST && a.inj_inc != nullptr;
+  if (!inject && a.n_steps > 0) draw_increments<E, IEEE, PF>(a, c, inc, u, (unsigned long long)s_first, chain_gid, scale, dscale);
+
   for (long long t = 0; t < a.n_steps; ++t) {
     const long long s = s_first + t;
-    // 1. proposal increments + accept uniform
-    float inc[E], u;
-    if (a.inj_inc != nullptr) {
+    // 1. proposal increments + accept uniform for this step (test mode) / for the next step (pipelined)
+    float inc_n[E], u_n = 0.0f;
+    if (inject) {
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int i = c.base + e;
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       }
       u = a.inj_u[t * a.n_chains + chain];
     } else {
-      draw_increments<E, IEEE>(a, c, inc, u, (unsigned long long)s, chain_gid, scale, dscale);
+      draw_increments<E, IEEE, PF>(a, c, inc_n, u_n, (unsigned long long)(s + 1), chain_gid, scale, dscale);
     }
     // 2. proposal, 3. its log-density
     float prop[E];
@@ -217,9 +228,9 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       x[e] = acc ? prop[e] : x[e];
     }
     lp = acc ? lpp : lp;
-    const bool post = s > a.burn_in;
+    const bool post = t >= burn_t;
     if (post) n_acc += acc ? 1u : 0u;
-    if (a.decisions != nullptr && lead) a.decisions[t * a.n_chains + chain] = acc ? 1 : 0;
+    if (TEST && a.decisions != nullptr && lead) a.decisions[t * a.n_chains + chain] = acc ? 1 : 0;
 
     // 6. adjacent-temperature sweep (whole ladder is in this CTA)
     if (K > 1) {
@@ -234,11 +245,12 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
         __syncthreads();
         const unsigned long long round_g = (unsigned long long)(a.rounds_before + round_local);  // 0-based
         const long long su_base = (round_local * a.n_ladders + ladder) * (K - 1);
+        const bool inj_su = TEST && a.inj_su != nullptr;
         if (a.swap_mode == RWMPT_SWAP_REFERENCE) {
           // decisions of all pairs are independent here: pair j only ever rewrites slot j
           bool ok = false;
           if (valid && temp < K - 1) {
-            const float us = a.inj_su ? a.inj_su[su_base + temp] : swap_uniform(a, ladder_gid, round_g, temp);
+            const float us = inj_su ? a.inj_su[su_base + temp] : swap_uniform(a.key0, a.key1, ladder_gid, round_g, temp);
             ok = swap_accept<IEEE>(beta, s_beta[cl + 1], s_lp[cl], s_lp[cl + 1], us);
             if (ok) {
 #pragma unroll
@@ -246,7 +258,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
                 if (c.base + e < d) x[e] = s_x[(cl + 1) * d + c.base + e];
               lp = s_lp[cl + 1];
             }
-            if (lead && a.swap_dec) a.swap_dec[su_base + temp] = ok ? 1 : 0;
+            if (TEST && lead && a.swap_dec) a.swap_dec[su_base + temp] = ok ? 1 : 0;
           }
           if (ok) { n_swap_acc++; last_attempt = round_g * (unsigned long long)(K - 1) + temp + 1; }
         } else {
@@ -254,11 +266,11 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
           if (valid && temp == 0 && c.sub == 0) {
             for (int j = 0; j < K - 1; ++j) {
               const int sa = s_src[cl + j], sb = s_src[cl + j + 1];
-              const float us = a.inj_su ? a.inj_su[su_base + j] : swap_uniform(a, ladder_gid, round_g, j);
+              const float us = inj_su ? a.inj_su[su_base + j] : swap_uniform(a.key0, a.key1, ladder_gid, round_g, j);
               const bool ok = swap_accept<IEEE>(s_beta[cl + j], s_beta[cl + j + 1], s_lp[sa], s_lp[sb], us);
               if (ok) { s_src[cl + j] = sb; s_src[cl + j + 1] = sa; }
               s_ok[cl + j] = ok ? 1 : 0;
-              if (a.swap_dec) a.swap_dec[su_base + j] = ok ? 1 : 0;
+              if (TEST && a.swap_dec) a.swap_dec[su_base + j] = ok ? 1 : 0;
             }
           }
           __syncthreads();
@@ -304,11 +316,16 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       }
       store_cd--;
     }
+    if (!inject) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) inc[e] = inc_n[e];
+      u = u_n;
+    }
   }
 
   // epilogue: state, log-density, accumulators
   jump_d += (double)jump_f;
-  jump_d = group_sum_f64(jump_d, W);
+  jump_d = group_sum_f64_w<WT>(jump_d, W);
   if (valid) {
 #pragma unroll
     for (int e = 0; e < E; ++e)

@@ -10,9 +10,9 @@ namespace rwmpt {
 #define RWMPT_FAST_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
 #define RWMPT_IEEE_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
 
-template <template <int, bool> class Target, int E, bool IEEE>
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool TEST>
 cudaError_t launch_mcmc_one(const KernelArgs& a, const LaunchGeom& g, cudaStream_t st) {
-  auto kern = mcmc_kernel<Target, E, IEEE>;
+  auto kern = mcmc_kernel<Target, E, IEEE, WT, PF, TEST>;
   if (g.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
@@ -32,17 +32,28 @@ cudaError_t launch_logp_one(const float* P, int d, int W, const float* x, long l
   return cudaGetLastError();
 }
 
+// Tuned variants (lanes-per-chain and proposal family fixed at compile time) exist for the BASELINE workloads; each
+// family's translation unit lists its own in Tuned<Target>::launch and returns cudaErrorNotSupported otherwise.
+template <template <int, bool> class Target>
+struct Tuned {
+  static cudaError_t launch(const KernelArgs&, const LaunchGeom&, cudaStream_t) { return cudaErrorNotSupported; }
+};
+
+// generic variants: runtime lanes-per-chain and proposal family.  IEEE kernels carry the test mode (injection,
+// decision outputs); fast kernels do not.
 template <template <int, bool> class Target>
 cudaError_t launch_mcmc_family(const KernelArgs& a, const LaunchGeom& g, bool ieee, cudaStream_t st) {
   if (ieee) {
     switch (g.E) {
-#define X(e) case e: return launch_mcmc_one<Target, e, true>(a, g, st);
+#define X(e) case e: return launch_mcmc_one<Target, e, true, 0, -1, true>(a, g, st);
       RWMPT_IEEE_E_LIST(X)
 #undef X
     }
   } else {
+    cudaError_t e = Tuned<Target>::launch(a, g, st);
+    if (e != cudaErrorNotSupported) return e;
     switch (g.E) {
-#define X(e) case e: return launch_mcmc_one<Target, e, false>(a, g, st);
+#define X(e) case e: return launch_mcmc_one<Target, e, false, 0, -1, false>(a, g, st);
       RWMPT_FAST_E_LIST(X)
 #undef X
     }
@@ -89,6 +100,20 @@ cudaError_t launch_logp_family(const float* P, int d, int E, int W, const float*
                                  bool ieee, cudaStream_t st);
 RWMPT_FAMILY_LIST(X)
 #undef X
+
+// RWMPT_DEFINE_TUNED(cls, LIST) with LIST(X) = X(E, W, PF) ... specialises Tuned<cls>
+#define RWMPT_TUNED_CASE(cls, e, w, pf) \
+  if (g.E == e && g.W == w && a.prop_family == pf) return launch_mcmc_one<cls, e, false, w, pf, false>(a, g, st);
+#define RWMPT_DEFINE_TUNED(cls, LIST)                                                              \
+  namespace rwmpt {                                                                                \
+  template <>                                                                                      \
+  struct Tuned<cls> {                                                                              \
+    static cudaError_t launch(const KernelArgs& a, const LaunchGeom& g, cudaStream_t st) {         \
+      LIST(cls)                                                                                    \
+      return cudaErrorNotSupported;                                                                \
+    }                                                                                              \
+  };                                                                                               \
+  }
 
 #define RWMPT_DEFINE_FAMILY(name, cls)                                                                        \
   namespace rwmpt {                                                                                           \

@@ -22,7 +22,8 @@ struct RoughCarpet {
   bool has_s;
   float s[E];
 
-  __device__ __forceinline__ void init(const Ctx& c) {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) {
     const float* P = c.P;
     m0 = P[0]; m1 = P[1]; m2 = P[2];
     lw0 = P[3]; lw1 = P[4]; lw2 = P[5];
@@ -37,7 +38,8 @@ struct RoughCarpet {
     }
   }
 
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     if constexpr (IEEE) {
       float part = 0.0f;
 #pragma unroll
@@ -52,7 +54,7 @@ struct RoughCarpet {
         const float L = M::add(M::log(ss), mx);
         if (c.base + e < c.d) part = M::add(part, L);
       }
-      return M::add(group_sum(part, c.W), J);
+      return M::add(group_sum(part, c), J);
     } else {
       // work in base 2; sum_i log(sum_k exp(t_ik)) = sum_i max_i + log(prod_i sum_k exp(t_ik - max_i)):
       // one lg2 per lane instead of one per coordinate.
@@ -71,7 +73,7 @@ struct RoughCarpet {
         }
       }
       const float part = (hi + lg2_approx(prod)) * kLn2;
-      return group_sum(part, c.W) + J;
+      return group_sum(part, c) + J;
     }
   }
 };
@@ -85,7 +87,8 @@ struct ThreeMixture {
   float mu[3][E];
   float s[E];
 
-  __device__ __forceinline__ void init(const Ctx& c) {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) {
     const float* P = c.P;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { lw[k] = P[k]; c1[k] = P[3 + k]; }
@@ -101,7 +104,8 @@ struct ThreeMixture {
     }
   }
 
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     float q[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -117,7 +121,7 @@ struct ThreeMixture {
     float t[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const float qq = group_sum(q[k], c.W);
+      const float qq = group_sum(q[k], c);
       float v = M::add(M::mul(-0.5f, qq), c1[k]);
       if (scaled) v = M::add(v, J);
       t[k] = M::add(v, lw[k]);
@@ -136,7 +140,8 @@ struct FullRosenbrock {
   float a, b;
   float mu[E];
 
-  __device__ __forceinline__ void init(const Ctx& c) {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) {
     a = c.P[0]; b = c.P[1];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -145,7 +150,8 @@ struct FullRosenbrock {
     }
   }
 
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     const float xn_lane = from_next_lane(x[0]);  // x[(sub+1)*E]; masked below when it does not exist
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
@@ -160,9 +166,9 @@ struct FullRosenbrock {
       }
     }
     if constexpr (IEEE) {
-      return -M::add(group_sum(s1, c.W), group_sum(s2, c.W));
+      return -M::add(group_sum(s1, c), group_sum(s2, c));
     } else {
-      return -group_sum(s1 + s2, c.W);
+      return -group_sum(s1 + s2, c);
     }
   }
 };
@@ -174,7 +180,8 @@ struct EvenRosenbrock {
   float a, b;
   float mu[E];
 
-  __device__ __forceinline__ void init(const Ctx& c) {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) {
     a = c.P[0]; b = c.P[1];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -183,7 +190,8 @@ struct EvenRosenbrock {
     }
   }
 
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     const float xn_lane = from_next_lane(x[0]);
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
@@ -198,9 +206,9 @@ struct EvenRosenbrock {
       }
     }
     if constexpr (IEEE) {
-      return -M::add(group_sum(s1, c.W), group_sum(s2, c.W));
+      return -M::add(group_sum(s1, c), group_sum(s2, c));
     } else {
-      return -group_sum(s1 + s2, c.W);
+      return -group_sum(s1 + s2, c);
     }
   }
 };
@@ -213,7 +221,8 @@ struct HybridRosenbrock {
   unsigned first_mask;  // bit e set: coordinate is the first of its block (depends on x_0^2)
   unsigned valid_mask;  // bit e set: coordinate index in [1, d)
 
-  __device__ __forceinline__ void init(const Ctx& c) {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) {
     a = c.P[0]; b = c.P[1]; mu = c.P[2];
     const int n1 = (int)c.P[3];
     const int blk = n1 - 1;
@@ -228,7 +237,8 @@ struct HybridRosenbrock {
     }
   }
 
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     const float x0 = from_leader(x[0], c);
     const float xp_lane = from_prev_lane(x[E - 1]);
     const float x0sq = M::sq(x0);
@@ -241,7 +251,7 @@ struct HybridRosenbrock {
       if ((valid_mask >> e) & 1u) part = M::add(part, t);
     }
     const float head = M::mul(-a, M::sq(M::sub(x0, mu)));
-    return M::sub(head, group_sum(part, c.W));
+    return M::sub(head, group_sum(part, c));
   }
 };
 
@@ -251,11 +261,13 @@ struct NealFunnel {
   using M = Mth<IEEE>;
   float mu_v, sv, mu_z, lsv, l2p, dm1;
 
-  __device__ __forceinline__ void init(const Ctx& c) {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) {
     mu_v = c.P[0]; sv = c.P[1]; mu_z = c.P[2]; lsv = c.P[3]; l2p = c.P[4]; dm1 = c.P[5];
   }
 
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     const float v = from_leader(x[0], c);
     float q = 0.0f;
 #pragma unroll
@@ -264,7 +276,7 @@ struct NealFunnel {
       const float dz = M::sub(x[e], mu_z);
       if (i >= 1 && i < c.d) q = IEEE ? M::add(q, M::mul(dz, dz)) : fmaf(dz, dz, q);
     }
-    q = group_sum(q, c.W);
+    q = group_sum(q, c);
     const float prior = M::sub(M::sub(M::mul(-0.5f, l2p), M::mul(0.5f, lsv)),
                                M::div(M::mul(0.5f, M::sq(M::sub(v, mu_v))), sv));
     if (c.d == 1) return prior;
@@ -278,13 +290,15 @@ struct NealFunnel {
 template <int E, bool IEEE>
 struct Hypercube {
   float L, R, lud;
-  __device__ __forceinline__ void init(const Ctx& c) { L = c.P[0]; R = c.P[1]; lud = c.P[2]; }
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) { L = c.P[0]; R = c.P[1]; lud = c.P[2]; }
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     float outside = 0.0f;
 #pragma unroll
     for (int e = 0; e < E; ++e)
       if (c.base + e < c.d && !(x[e] >= L && x[e] <= R)) outside += 1.0f;
-    return group_sum(outside, c.W) == 0.0f ? lud : RWMPT_NEG_INF;
+    return group_sum(outside, c) == 0.0f ? lud : RWMPT_NEG_INF;
   }
 };
 
@@ -293,8 +307,10 @@ template <int E, bool IEEE>
 struct IIDGamma {
   using M = Mth<IEEE>;
   float k, th, lnc;
-  __device__ __forceinline__ void init(const Ctx& c) { k = c.P[0]; th = c.P[1]; lnc = c.P[2]; }
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) { k = c.P[0]; th = c.P[1]; lnc = c.P[2]; }
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     float part = 0.0f;
     const float km1 = M::sub(k, 1.0f);
 #pragma unroll
@@ -306,7 +322,7 @@ struct IIDGamma {
         part = ok ? M::add(part, t) : RWMPT_NEG_INF;
       }
     }
-    return M::sub(group_sum(part, c.W), lnc);
+    return M::sub(group_sum(part, c), lnc);
   }
 };
 
@@ -315,8 +331,10 @@ template <int E, bool IEEE>
 struct IIDBeta {
   using M = Mth<IEEE>;
   float al, be, lnc;
-  __device__ __forceinline__ void init(const Ctx& c) { al = c.P[0]; be = c.P[1]; lnc = c.P[2]; }
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) { al = c.P[0]; be = c.P[1]; lnc = c.P[2]; }
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     float part = 0.0f;
     const float am1 = M::sub(al, 1.0f), bm1 = M::sub(be, 1.0f);
 #pragma unroll
@@ -328,7 +346,7 @@ struct IIDBeta {
         part = ok ? M::add(part, t) : RWMPT_NEG_INF;
       }
     }
-    return M::add(group_sum(part, c.W), lnc);
+    return M::add(group_sum(part, c), lnc);
   }
 };
 
@@ -338,7 +356,8 @@ struct ScaledMVN {
   using M = Mth<IEEE>;
   float lnc;
   float cc[E];
-  __device__ __forceinline__ void init(const Ctx& c) {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) {
     lnc = c.P[0];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -346,14 +365,15 @@ struct ScaledMVN {
       cc[e] = (i < c.d) ? c.P[RWMPT_PARAM_HEADER + i] : 0.0f;
     }
   }
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     float part = 0.0f;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const float sx = M::mul(cc[e], x[e]);
       if (c.base + e < c.d) part = IEEE ? M::add(part, M::mul(sx, sx)) : fmaf(sx, sx, part);
     }
-    return M::sub(lnc, M::mul(0.5f, group_sum(part, c.W)));
+    return M::sub(lnc, M::mul(0.5f, group_sum(part, c)));
   }
 };
 
@@ -363,7 +383,8 @@ struct MVNDiag {
   using M = Mth<IEEE>;
   float lnc;
   float mean[E], prec[E];
-  __device__ __forceinline__ void init(const Ctx& c) {
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) {
     lnc = c.P[0];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -372,7 +393,8 @@ struct MVNDiag {
       prec[e] = (i < c.d) ? c.P[RWMPT_PARAM_HEADER + c.d + i] : 0.0f;
     }
   }
-  __device__ __forceinline__ float logp(const float (&x)[E], const Ctx& c) const {
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     float part = 0.0f;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -380,7 +402,7 @@ struct MVNDiag {
       const float t = M::mul(M::mul(cen, prec[e]), cen);
       if (c.base + e < c.d) part = M::add(part, t);
     }
-    return M::add(M::mul(-0.5f, group_sum(part, c.W)), lnc);
+    return M::add(M::mul(-0.5f, group_sum(part, c)), lnc);
   }
 };
 
