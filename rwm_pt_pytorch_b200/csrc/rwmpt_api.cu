@@ -195,6 +195,10 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   a.rounds_before = count_rounds(0, r->step_offset, r->burn_in, a.swap_every);
   a.state = r->state; a.logp = r->logp;
   a.key0 = (unsigned)(r->seed & 0xffffffffu); a.key1 = (unsigned)(r->seed >> 32);
+  for (int q = 0; q < 10; ++q) {
+    a.rk[2 * q] = a.key0 + (unsigned)q * 0x9E3779B9u;
+    a.rk[2 * q + 1] = a.key1 + (unsigned)q * 0xBB67AE85u;
+  }
   a.chain_id_base = r->chain_id_base;
   a.samples = r->samples; a.sample_logp = r->sample_logp;
   a.store_start = r->store_start; a.thin = r->thin < 1 ? 1 : r->thin; a.sample_stride = r->sample_stride; a.sample_rows = r->sample_rows;

@@ -33,6 +33,7 @@ struct KernelArgs {
   float* state;
   float* logp;
   unsigned int key0, key1;
+  unsigned int rk[20];  // Philox round keys (key0 + r*W0, key1 + r*W1), r = 0..9
   long long chain_id_base;
   float* samples;
   float* sample_logp;
@@ -178,9 +179,14 @@ __device__ __forceinline__ double group_sum_f64_w(double v, int W) {
 }
 
 // Per-thread view of where it sits inside its chain.
-template <int WT_>
+template <int WT_, bool EXACT_>
 struct CtxT {
   static constexpr int WT = WT_;
+  static constexpr bool EXACT = EXACT_;  // E * W == d: no padding coordinates, masks fold away
+  __device__ __forceinline__ bool ok(int e) const {
+    if constexpr (EXACT_) return true;
+    else return base + e < d;
+  }
   const float* P;  // target params
   int d;           // dimension
   int W;           // lanes per chain
@@ -189,7 +195,7 @@ struct CtxT {
   int lane;        // lane in warp
   int leader;      // lane (in warp) of sub == 0 of this chain
 };
-using Ctx = CtxT<0>;
+using Ctx = CtxT<0, false>;
 
 template <class C>
 __device__ __forceinline__ float group_sum(float v, const C& c) { return group_sum_w<C::WT>(v, c.W); }

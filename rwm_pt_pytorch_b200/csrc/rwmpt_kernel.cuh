@@ -22,9 +22,18 @@
 
 namespace rwmpt {
 
-// ---- normal pair from two Philox words ---------------------------------------------------------
+// ---- Philox with the 10 round keys precomputed on the host (uniform operands from the argument block) -----
+__device__ __forceinline__ uint4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const KernelArgs& a) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, a.rk[2 * r], a.rk[2 * r + 1]);
+  uint4 o;
+  o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+
+// ---- normal pair from two Philox words; `rs2` = -2 ln2 * scale^2 folds the proposal std into the radius ----
 template <bool IEEE>
-__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1) {
+__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1, float rs2 = -2.0f * kLn2) {
   const float u1 = u01_open_low(wa);
   if constexpr (IEEE) {
     const float r = sqrtf(-2.0f * logf(u1));
@@ -33,67 +42,84 @@ __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, 
     z0 = r * cs;
     z1 = r * sn;
   } else {
-    const float r = sqrt_approx(-2.0f * kLn2 * lg2_approx(u1));
+    const float r = sqrt_approx(rs2 * lg2_approx(u1));
     const float th = (float)wb * 1.4629180792671596e-9f;  // 2*pi/2^32
     z0 = r * __cosf(th);
     z1 = r * __sinf(th);
   }
 }
 
-__host__ __device__ constexpr int philox_calls_per_step(int E) { return (E + 2 + 3) / 4; }
+// Words one lane needs for TWO consecutive steps: 2E normals/uniforms + 2 accept uniforms (+ 2 ball radii).
+__host__ __device__ constexpr int pair_words(int E, int PF) {
+  return 2 * E + 2 + ((PF == RWMPT_P_NORMAL || PF == RWMPT_P_LAPLACE) ? 0 : 2);
+}
 
-// Raw per-step randomness of one lane: E standard normals or E uniforms, plus the chain's accept uniform
-// and (UniformRadius) radius uniform, both taken from the leader lane.  PF >= 0: proposal family known at
-// compile time (no per-step branch); PF < 0: runtime switch on a.prop_family.
+// Randomness of one lane for the two steps of pair `pair` (global steps 2*pair+1 and 2*pair+2): increments after
+// scaling, and the chain's accept uniforms (taken from the leader lane).  Drawing two steps at once uses every
+// Philox word (E=5, Normal: 3 calls per 2 steps) and gives the scheduler three independent Philox chains.
+// PF >= 0: proposal family known at compile time; PF < 0: runtime switch on a.prop_family.
 template <int E, bool IEEE, int PF, class C>
-__device__ __forceinline__ void draw_increments(const KernelArgs& a, const C& c, float (&inc)[E], float& u_acc,
-                                                unsigned long long s, unsigned long long chain_gid, float scale,
-                                                const float (&dscale)[E]) {
-  constexpr int NC = philox_calls_per_step(E);
+__device__ __forceinline__ void draw_pair(const KernelArgs& a, const C& c, float (&incA)[E], float (&incB)[E], float& uA,
+                                          float& uB, unsigned long long pair, unsigned long long chain_gid, float scale,
+                                          const float (&dscale)[E]) {
+  constexpr int NW = pair_words(E, PF);
+  constexpr int NC = (NW + 3) / 4;
   const int pf = PF >= 0 ? PF : a.prop_family;
   uint32_t w[4 * NC];
-  const uint32_t c0 = (uint32_t)s;
-  const uint32_t c1hi = ((uint32_t)(s >> 32) << 16) | ((uint32_t)c.sub << 8);
+  const uint32_t c0 = (uint32_t)pair;
+  const uint32_t c1hi = ((uint32_t)(pair >> 32) << 16) | ((uint32_t)c.sub << 8);
 #pragma unroll
   for (int k = 0; k < NC; ++k) {
-    const uint4 r = philox4x32_10(c0, c1hi | (uint32_t)k, (uint32_t)chain_gid, (uint32_t)(chain_gid >> 32), a.key0, a.key1);
+    const uint4 r = philox_rk(c0, c1hi | (uint32_t)k, (uint32_t)chain_gid, (uint32_t)(chain_gid >> 32), a);
     w[4 * k + 0] = r.x; w[4 * k + 1] = r.y; w[4 * k + 2] = r.z; w[4 * k + 3] = r.w;
   }
-  u_acc = from_leader(u01_from_bits(w[4 * NC - 1]), c);
+  uA = from_leader(u01_from_bits(w[4 * NC - 1]), c);
+  uB = from_leader(u01_from_bits(w[4 * NC - 2]), c);
   if (pf == RWMPT_P_LAPLACE) {
     // laplace.py:47-69: u in (-.5,.5); -s * sign(u) * log1p(max(-2|u|, -0.999999))
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
+    for (int e = 0; e < 2 * E; ++e) {
       const float u = u01_from_bits(w[e]) - 0.5f;
       const float arg = fmaxf(-2.0f * fabsf(u), -0.999999f);
       const float l = IEEE ? log1pf(arg) : lg2_approx(1.0f + arg) * kLn2;
       const float sg = (u > 0.0f) ? 1.0f : ((u < 0.0f) ? -1.0f : 0.0f);
-      inc[e] = -(scale * dscale[e]) * sg * l;
+      const float v = -(scale * dscale[e < E ? e : e - E]) * sg * l;
+      if (e < E) incA[e] = v; else incB[e - E] = v;
     }
     return;
   }
-  float z[E + 1];
+  float z[2 * E];
+  const bool fold = !IEEE && pf == RWMPT_P_NORMAL;  // normal.py:47-55: randn * std
+  const float rs2 = fold ? -2.0f * kLn2 * scale * scale : -2.0f * kLn2;
 #pragma unroll
-  for (int p = 0; p < (E + 1) / 2; ++p) box_muller<IEEE>(w[2 * p], w[2 * p + 1], z[2 * p], z[2 * p + 1]);
+  for (int p = 0; p < E; ++p) box_muller<IEEE>(w[2 * p], w[2 * p + 1], z[2 * p], z[2 * p + 1], rs2);
   if (pf == RWMPT_P_NORMAL) {
-    // normal.py:47-55: randn * std
 #pragma unroll
-    for (int e = 0; e < E; ++e) inc[e] = z[e] * scale;
+    for (int e = 0; e < E; ++e) {
+      incA[e] = fold ? z[e] : z[e] * scale;
+      incB[e] = fold ? z[E + e] : z[E + e] * scale;
+    }
   } else {
     // uniform.py:48-73: z/||z|| * R * u^(1/d)
-    float n2 = 0.0f;
+    float nA = 0.0f, nB = 0.0f;
 #pragma unroll
     for (int e = 0; e < E; ++e)
-      if (c.base + e < c.d) n2 = fmaf(z[e], z[e], n2);
-    n2 = group_sum(n2, c);
-    const float nrm = IEEE ? sqrtf(n2) : sqrt_approx(n2);
-    const float safe = nrm > 1e-12f ? nrm : 1.0f;
-    const float ur = from_leader(u01_from_bits(w[4 * NC - 2]), c);
+      if (c.ok(e)) { nA = fmaf(z[e], z[e], nA); nB = fmaf(z[E + e], z[E + e], nB); }
+    nA = group_sum(nA, c);
+    nB = group_sum(nB, c);
     const float inv_d = 1.0f / (float)c.d;
-    const float rad = IEEE ? scale * powf(ur, inv_d) : scale * ex2_approx(lg2_approx(ur) * inv_d);
-    const float f = IEEE ? rad / safe : rad * rcp_approx(safe);
+    float f[2];
 #pragma unroll
-    for (int e = 0; e < E; ++e) inc[e] = z[e] * f;
+    for (int h = 0; h < 2; ++h) {
+      const float n2 = h ? nB : nA;
+      const float nrm = IEEE ? sqrtf(n2) : sqrt_approx(n2);
+      const float safe = nrm > 1e-12f ? nrm : 1.0f;
+      const float ur = from_leader(u01_from_bits(w[4 * NC - 3 - h]), c);
+      const float rad = IEEE ? scale * powf(ur, inv_d) : scale * ex2_approx(lg2_approx(ur) * inv_d);
+      f[h] = IEEE ? rad / safe : rad * rcp_approx(safe);
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) { incA[e] = z[e] * f[0]; incB[e] = z[E + e] * f[1]; }
   }
 }
 
@@ -117,8 +143,9 @@ __device__ __forceinline__ bool swap_accept(float bj, float bk, float lj, float 
 }
 
 // Template parameters: Target functor; E coordinates per lane; IEEE parity arithmetic; WT lanes per chain (0 = runtime);
-// PF proposal family (-1 = runtime); TEST = injected randomness / decision outputs available (not software-pipelined).
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool TEST>
+// PF proposal family (-1 = runtime); EXACT: E*W == dim (no padding masks); TEST: injected randomness / decision
+// outputs available.
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
 __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a) {
   using M = Mth<IEEE>;
   extern __shared__ float smem[];
@@ -126,7 +153,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
   const int W = WT > 0 ? WT : a.W;
   const int K = a.K, d = a.dim;
   const int cl = threadIdx.x / W;  // chain within CTA
-  CtxT<WT> c;
+  CtxT<WT, EXACT> c;
   c.P = a.P; c.d = d; c.W = W;
   c.sub = threadIdx.x % W;
   c.base = c.sub * E;
@@ -173,7 +200,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
   long long swap_cd = -1;
   if (K > 1) {
     long long nxt = ((s_first + a.swap_every - 1) / a.swap_every) * a.swap_every;
-    while (nxt <= a.burn_in) nxt += a.swap_every;
+    if (nxt <= a.burn_in) nxt = (a.burn_in / a.swap_every + 1) * a.swap_every;
     swap_cd = nxt - s_first;
   }
   long long store_cd = -1, store_m = 0;
@@ -188,34 +215,17 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
   const long long burn_t = a.burn_in > a.step_offset ? a.burn_in - a.step_offset : 0;  // local steps t >= burn_t count
 
   unsigned long long n_acc = 0, n_swap_acc = 0, last_attempt = 0;
+  unsigned n_acc32 = 0;
   long long round_local = 0;
   float jump_f = 0.0f;
   double jump_d = 0.0;
 
-  // software pipeline: the increments of step t+1 are drawn while step t's density / reduction / accept chain
-  // is in flight (they do not depend on the state), which doubles the independent work a warp can issue.
-  float inc[E], u = 0.0f;
-  const bool inject = TEST && a.inj_inc != nullptr;
-  if (!inject && a.n_steps > 0) draw_increments<E, IEEE, PF>(a, c, inc, u, (unsigned long long)s_first, chain_gid, scale, dscale);
-
-  for (long long t = 0; t < a.n_steps; ++t) {
-    const long long s = s_first + t;
-    // 1. proposal increments + accept uniform for this step (test mode) / for the next step (pipelined)
-    float inc_n[E], u_n = 0.0f;
-    if (inject) {
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int i = c.base + e;
-        inc[e] = (i < d) ? a.inj_inc[(t * a.n_chains + chain) * d + i] : 0.0f;
-      }
-      u = a.inj_u[t * a.n_chains + chain];
-    } else {
-      draw_increments<E, IEEE, PF>(a, c, inc_n, u_n, (unsigned long long)(s + 1), chain_gid, scale, dscale);
-    }
+  // ---- one Metropolis step (+ sweep, accumulators, retained sample) with the given increments -----------------
+  auto do_step = [&](const float (&inc)[E], const float u, const long long t) {
     // 2. proposal, 3. its log-density
     float prop[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) prop[e] = (c.base + e < d) ? M::add(x[e], inc[e]) : 0.0f;
+    for (int e = 0; e < E; ++e) prop[e] = c.ok(e) ? M::add(x[e], inc[e]) : 0.0f;
     const float lpp = tgt.logp(prop, c);
     // 4. accept rule (rwm_gpu_optimized.py:22-25): NaN compares false -> reject
     const float lar = M::mul(beta, M::sub(lpp, lp));
@@ -229,13 +239,15 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     }
     lp = acc ? lpp : lp;
     const bool post = t >= burn_t;
-    if (post) n_acc += acc ? 1u : 0u;
+    n_acc32 += (post && acc) ? 1u : 0u;
     if (TEST && a.decisions != nullptr && lead) a.decisions[t * a.n_chains + chain] = acc ? 1 : 0;
 
     // 6. adjacent-temperature sweep (whole ladder is in this CTA)
+    bool swapped_now = false;
     if (K > 1) {
       if (swap_cd == 0) {
         swap_cd = a.swap_every;
+        swapped_now = true;
         if (in_cta) {
 #pragma unroll
           for (int e = 0; e < E; ++e)
@@ -292,13 +304,24 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     }
 
     // 7. squared jump of this step (Metropolis move + swap move), s > burn_in
-    if (post) {
+    if (IEEE || swapped_now) {
+      // exactly the reference's chain[t+1] - chain[t] (rwm_gpu_optimized.py:531)
+      float j2 = 0.0f;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const float dx = M::sub(x[e], xo[e]);
-        jump_f = fmaf(dx, dx, jump_f);
+        j2 = fmaf(dx, dx, j2);
       }
-      if ((t & 63) == 63) { jump_d += (double)jump_f; jump_f = 0.0f; }
+      jump_f += post ? j2 : 0.0f;
+    } else {
+      float j2 = 0.0f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) j2 = c.ok(e) ? fmaf(inc[e], inc[e], j2) : j2;
+      jump_f += (post && acc) ? j2 : 0.0f;
+    }
+    if ((t & 63) == 63) {
+      jump_d += (double)jump_f; jump_f = 0.0f;
+      n_acc += n_acc32; n_acc32 = 0;
     }
 
     // 8. retained samples: layout (chain, row, dim)
@@ -316,15 +339,52 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       }
       store_cd--;
     }
-    if (!inject) {
+  };
+
+  const bool inject = TEST && a.inj_inc != nullptr;
+  if (inject) {
+    if constexpr (TEST) {
+      for (long long t = 0; t < a.n_steps; ++t) {
+        float inc[E];
 #pragma unroll
-      for (int e = 0; e < E; ++e) inc[e] = inc_n[e];
-      u = u_n;
+        for (int e = 0; e < E; ++e) {
+          const int i = c.base + e;
+          inc[e] = (i < d) ? a.inj_inc[(t * a.n_chains + chain) * d + i] : 0.0f;
+        }
+        do_step(inc, a.inj_u[t * a.n_chains + chain], t);
+      }
+    }
+  } else if (a.n_steps > 0) {
+    // software pipeline: the increments of the NEXT pair of steps are drawn while the current pair's density /
+    // reduction / accept chain is in flight (they do not depend on the state).
+    float iA[E], iB[E], uA, uB;
+    unsigned long long pair = (unsigned long long)(s_first - 1) >> 1;
+    draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, pair, chain_gid, scale, dscale);
+    long long t = 0;
+    if ((s_first - 1) & 1) {  // the run starts on the second step of a pair
+      do_step(iB, uB, t);
+      ++t; ++pair;
+      draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, pair, chain_gid, scale, dscale);
+    }
+    while (t < a.n_steps) {
+      float nA[E], nB[E], vA, vB;
+      draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
+      do_step(iA, uA, t);
+      ++t;
+      if (t < a.n_steps) {
+        do_step(iB, uB, t);
+        ++t;
+      }
+      ++pair;
+#pragma unroll
+      for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
+      uA = vA; uB = vB;
     }
   }
 
   // epilogue: state, log-density, accumulators
   jump_d += (double)jump_f;
+  n_acc += n_acc32;
   jump_d = group_sum_f64_w<WT>(jump_d, W);
   if (valid) {
 #pragma unroll
@@ -346,7 +406,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) logp_kernel(const float* __res
                                                               long long n, float* __restrict__ out) {
   const int per_cta = blockDim.x / W;
   const int cl = threadIdx.x / W;
-  Ctx c;
+  CtxT<0, false> c;
   c.P = P; c.d = d; c.W = W;
   c.sub = threadIdx.x % W;
   c.base = c.sub * E;

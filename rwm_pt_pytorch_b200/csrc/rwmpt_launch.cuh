@@ -10,9 +10,9 @@ namespace rwmpt {
 #define RWMPT_FAST_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
 #define RWMPT_IEEE_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
 
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool TEST>
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
 cudaError_t launch_mcmc_one(const KernelArgs& a, const LaunchGeom& g, cudaStream_t st) {
-  auto kern = mcmc_kernel<Target, E, IEEE, WT, PF, TEST>;
+  auto kern = mcmc_kernel<Target, E, IEEE, WT, PF, EXACT, TEST>;
   if (g.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
@@ -45,7 +45,7 @@ template <template <int, bool> class Target>
 cudaError_t launch_mcmc_family(const KernelArgs& a, const LaunchGeom& g, bool ieee, cudaStream_t st) {
   if (ieee) {
     switch (g.E) {
-#define X(e) case e: return launch_mcmc_one<Target, e, true, 0, -1, true>(a, g, st);
+#define X(e) case e: return launch_mcmc_one<Target, e, true, 0, -1, false, true>(a, g, st);
       RWMPT_IEEE_E_LIST(X)
 #undef X
     }
@@ -53,7 +53,7 @@ cudaError_t launch_mcmc_family(const KernelArgs& a, const LaunchGeom& g, bool ie
     cudaError_t e = Tuned<Target>::launch(a, g, st);
     if (e != cudaErrorNotSupported) return e;
     switch (g.E) {
-#define X(e) case e: return launch_mcmc_one<Target, e, false, 0, -1, false>(a, g, st);
+#define X(e) case e: return launch_mcmc_one<Target, e, false, 0, -1, false, false>(a, g, st);
       RWMPT_FAST_E_LIST(X)
 #undef X
     }
@@ -102,8 +102,11 @@ RWMPT_FAMILY_LIST(X)
 #undef X
 
 // RWMPT_DEFINE_TUNED(cls, LIST) with LIST(X) = X(E, W, PF) ... specialises Tuned<cls>
-#define RWMPT_TUNED_CASE(cls, e, w, pf) \
-  if (g.E == e && g.W == w && a.prop_family == pf) return launch_mcmc_one<cls, e, false, w, pf, false>(a, g, st);
+#define RWMPT_TUNED_CASE(cls, e, w, pf)                                                        \
+  if (g.E == e && g.W == w && a.prop_family == pf) {                                          \
+    if (a.dim == e * w) return launch_mcmc_one<cls, e, false, w, pf, true, false>(a, g, st);  \
+    return launch_mcmc_one<cls, e, false, w, pf, false, false>(a, g, st);                     \
+  }
 #define RWMPT_DEFINE_TUNED(cls, LIST)                                                              \
   namespace rwmpt {                                                                                \
   template <>                                                                                      \

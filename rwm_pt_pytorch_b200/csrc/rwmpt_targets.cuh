@@ -18,7 +18,7 @@ template <int E, bool IEEE>
 struct RoughCarpet {
   using M = Mth<IEEE>;
   float m0, m1, m2, lw0, lw1, lw2, lsp, J;
-  float a0, a1, a2;  // fast path: (lw_k - lsp) * log2(e)
+  float b0, b1, b2, c0, c1, c2;  // fast path: b_k = log2(e) m_k, c_k = log2(e) (lw_k - lsp - m_k^2 / 2)
   bool has_s;
   float s[E];
 
@@ -30,7 +30,9 @@ struct RoughCarpet {
     lsp = P[6];
     has_s = P[7] != 0.0f;
     J = has_s ? P[8] : 0.0f;
-    a0 = (lw0 - lsp) * kLog2e; a1 = (lw1 - lsp) * kLog2e; a2 = (lw2 - lsp) * kLog2e;
+    b0 = kLog2e * m0; b1 = kLog2e * m1; b2 = kLog2e * m2;
+    c0 = kLog2e * (lw0 - lsp - 0.5f * m0 * m0); c1 = kLog2e * (lw1 - lsp - 0.5f * m1 * m1);
+    c2 = kLog2e * (lw2 - lsp - 0.5f * m2 * m2);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int i = c.base + e;
@@ -52,26 +54,27 @@ struct RoughCarpet {
         if (isinf(mx)) mx = 0.0f;  // torch.logsumexp masks infinite maxima
         const float ss = M::add(M::add(M::exp(M::sub(t0, mx)), M::exp(M::sub(t1, mx))), M::exp(M::sub(t2, mx)));
         const float L = M::add(M::log(ss), mx);
-        if (c.base + e < c.d) part = M::add(part, L);
+        if (c.ok(e)) part = M::add(part, L);
       }
       return M::add(group_sum(part, c), J);
     } else {
-      // work in base 2; sum_i log(sum_k exp(t_ik)) = sum_i max_i + log(prod_i sum_k exp(t_ik - max_i)):
-      // one lg2 per lane instead of one per coordinate.
-      float hi = 0.0f, prod = 1.0f;
-      constexpr float h = -0.5f * kLog2e;
+      // work in base 2.  t_k = h xs^2 + b_k xs + c_k (h = -log2(e)/2, b_k = log2(e) m_k, c_k = h m_k^2 + a_k): the
+      // quadratic term is common to the three modes, so logsumexp_k t_k = h xs^2 + logsumexp_k (b_k xs + c_k);
+      // and sum_i log2(S_i) = log2(prod_i S_i): one lg2 per lane instead of one per coordinate.
+      float hi = 0.0f, prod = 1.0f, q = 0.0f;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const float xs = x[e] * s[e];
-        const float d0 = xs - m0, d1 = xs - m1, d2 = xs - m2;
-        const float t0 = fmaf(d0 * h, d0, a0), t1 = fmaf(d1 * h, d1, a1), t2 = fmaf(d2 * h, d2, a2);
-        const float mx = fmaxf(fmaxf(t0, t1), t2);
-        const float ss = ex2_approx(t0 - mx) + ex2_approx(t1 - mx) + ex2_approx(t2 - mx);
-        if (c.base + e < c.d) {
+        const float l0 = fmaf(b0, xs, c0), l1 = fmaf(b1, xs, c1), l2 = fmaf(b2, xs, c2);
+        const float mx = fmaxf(fmaxf(l0, l1), l2);
+        const float ss = ex2_approx(l0 - mx) + ex2_approx(l1 - mx) + ex2_approx(l2 - mx);
+        q = fmaf(xs, xs, q);  // padding coordinates hold xs = 0
+        if (c.ok(e)) {
           hi += mx;
           prod *= ss;
         }
       }
+      hi = fmaf(-0.5f * kLog2e, q, hi);
       const float part = (hi + lg2_approx(prod)) * kLn2;
       return group_sum(part, c) + J;
     }
@@ -110,7 +113,7 @@ struct ThreeMixture {
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const float xs = scaled ? M::mul(x[e], s[e]) : x[e];
-      if (c.base + e < c.d) {
+      if (c.ok(e)) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const float dd = M::sub(xs, mu[k][e]);
@@ -297,7 +300,7 @@ struct Hypercube {
     float outside = 0.0f;
 #pragma unroll
     for (int e = 0; e < E; ++e)
-      if (c.base + e < c.d && !(x[e] >= L && x[e] <= R)) outside += 1.0f;
+      if (c.ok(e) && !(x[e] >= L && x[e] <= R)) outside += 1.0f;
     return group_sum(outside, c) == 0.0f ? lud : RWMPT_NEG_INF;
   }
 };
@@ -315,7 +318,7 @@ struct IIDGamma {
     const float km1 = M::sub(k, 1.0f);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      if (c.base + e < c.d) {
+      if (c.ok(e)) {
         const bool ok = x[e] > 0.0f;
         const float xx = ok ? x[e] : 1.0f;
         const float t = M::sub(M::mul(km1, M::log(xx)), M::div(xx, th));
@@ -339,7 +342,7 @@ struct IIDBeta {
     const float am1 = M::sub(al, 1.0f), bm1 = M::sub(be, 1.0f);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      if (c.base + e < c.d) {
+      if (c.ok(e)) {
         const bool ok = x[e] > 0.0f && x[e] < 1.0f;
         const float xx = ok ? x[e] : 0.5f;
         const float t = M::add(M::mul(am1, M::log(xx)), M::mul(bm1, M::log(M::sub(1.0f, xx))));
@@ -371,7 +374,7 @@ struct ScaledMVN {
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const float sx = M::mul(cc[e], x[e]);
-      if (c.base + e < c.d) part = IEEE ? M::add(part, M::mul(sx, sx)) : fmaf(sx, sx, part);
+      if (c.ok(e)) part = IEEE ? M::add(part, M::mul(sx, sx)) : fmaf(sx, sx, part);
     }
     return M::sub(lnc, M::mul(0.5f, group_sum(part, c)));
   }
@@ -400,7 +403,7 @@ struct MVNDiag {
     for (int e = 0; e < E; ++e) {
       const float cen = M::sub(x[e], mean[e]);
       const float t = M::mul(M::mul(cen, prec[e]), cen);
-      if (c.base + e < c.d) part = M::add(part, t);
+      if (c.ok(e)) part = M::add(part, t);
     }
     return M::add(M::mul(-0.5f, group_sum(part, c)), lnc);
   }
