@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     const float lpp = tgt.logp(prop, c);
     // 4. accept rule (rwm_gpu_optimized.py:22-25): NaN compares false -> reject
     const float lar = M::mul(beta, M::sub(lpp, lp));
-    const bool acc = (lar > 0.0f) || (u < M::exp(lar));
+    const bool acc = (lar > 0.0f) | (u < M::exp(lar));  // bitwise: no short-circuit branch
     // 5. select
     float xo[E];
 #pragma unroll
@@ -341,6 +341,37 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     }
   };
 
+  // ---- plain step: no sweep, no retained sample, no flush -- a single basic block, so that ptxas can interleave it
+  // with the Philox / Box-Muller stream of the next pair of steps.  `post` is invariant between events.
+  auto plain_step = [&](const float (&inc)[E], const float u, const bool post) {
+    float prop[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) prop[e] = c.ok(e) ? M::add(x[e], inc[e]) : 0.0f;
+    const float lpp = tgt.logp(prop, c);
+    const float lar = M::mul(beta, M::sub(lpp, lp));
+    const bool acc = (lar > 0.0f) | (u < M::exp(lar));
+    float j2 = 0.0f;
+    if constexpr (IEEE) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float xn = acc ? prop[e] : x[e];
+        const float dx = M::sub(xn, x[e]);
+        j2 = fmaf(dx, dx, j2);
+        x[e] = xn;
+      }
+      jump_f += post ? j2 : 0.0f;
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        j2 = c.ok(e) ? fmaf(inc[e], inc[e], j2) : j2;
+        x[e] = acc ? prop[e] : x[e];
+      }
+      jump_f += (post & acc) ? j2 : 0.0f;
+    }
+    lp = acc ? lpp : lp;
+    n_acc32 += (post & acc) ? 1u : 0u;
+  };
+
   const bool inject = TEST && a.inj_inc != nullptr;
   if (inject) {
     if constexpr (TEST) {
@@ -355,8 +386,10 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       }
     }
   } else if (a.n_steps > 0) {
-    // software pipeline: the increments of the NEXT pair of steps are drawn while the current pair's density /
-    // reduction / accept chain is in flight (they do not depend on the state).
+    // Software pipeline: the increments of the NEXT pair of steps are drawn while the current pair's density /
+    // reduction / accept chain is in flight (they do not depend on the state).  Steps with an "event" (sweep due,
+    // sample to retain, accumulator flush, burn-in boundary, end of run) go through do_step; all other pairs run
+    // plain_step twice with no branch at all.
     float iA[E], iB[E], uA, uB;
     unsigned long long pair = (unsigned long long)(s_first - 1) >> 1;
     draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, pair, chain_gid, scale, dscale);
@@ -367,18 +400,42 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, pair, chain_gid, scale, dscale);
     }
     while (t < a.n_steps) {
-      float nA[E], nB[E], vA, vB;
-      draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
-      do_step(iA, uA, t);
-      ++t;
-      if (t < a.n_steps) {
-        do_step(iB, uB, t);
-        ++t;
-      }
-      ++pair;
+      // first local step >= t that needs the general path
+      long long ev = t | 63;                                   // accumulator flush
+      if (a.n_steps - 1 < ev) ev = a.n_steps - 1;              // last step (also covers an odd tail)
+      if (t < burn_t && burn_t - 1 < ev) ev = burn_t - 1;      // burn-in boundary inside a pair
+      if (K > 1 && t + swap_cd < ev) ev = t + swap_cd;         // sweep due after that step
+      if (a.samples != nullptr && t + store_cd < ev) ev = t + store_cd;
+      const bool post = t >= burn_t;
+      const long long n_fast = (ev - t) >> 1;                  // whole pairs strictly before the event
+      for (long long q = 0; q < n_fast; ++q) {
+        float nA[E], nB[E], vA, vB;
+        draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
+        plain_step(iA, uA, post);
+        plain_step(iB, uB, post);
+        ++pair;
 #pragma unroll
-      for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
-      uA = vA; uB = vB;
+        for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
+        uA = vA; uB = vB;
+      }
+      t += 2 * n_fast;
+      if (K > 1) swap_cd -= 2 * n_fast;
+      if (a.samples != nullptr) store_cd -= 2 * n_fast;
+      // the pair that holds the event, through the general path
+      {
+        float nA[E], nB[E], vA, vB;
+        draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
+        do_step(iA, uA, t);
+        ++t;
+        if (t < a.n_steps) {
+          do_step(iB, uB, t);
+          ++t;
+        }
+        ++pair;
+#pragma unroll
+        for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
+        uA = vA; uB = vB;
+      }
     }
   }
 
