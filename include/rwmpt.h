@@ -177,6 +177,10 @@ int rwmpt_esjd_reduce(const float* samples, int64_t n_chains, int64_t stride, in
  * the denominators of the FP32 / SFU rooflines of SURVEY.md section 8(d).  fp32_tflops counts an FMA as 2 flops. */
 int rwmpt_probe_peaks(double* fp32_tflops, double* sfu_gops);
 
+/* Warp-instruction issue rate (warp-instr/s, whole GPU) of a dependent-free loop at a chosen occupancy:
+ * kind 0 FFMA, 1 MUFU.EX2, 2 Philox rounds (IMAD/LOP3).  Diagnostic used by scripts/gpu_issue_probe.py. */
+int rwmpt_probe_issue(int kind, int blocks, int threads, int iters, double* ops_per_s);
+
 /* Philox4x32-10 known-answer hook (host in / host out, runs one device thread). */
 int rwmpt_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

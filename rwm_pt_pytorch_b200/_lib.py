@@ -9,7 +9,7 @@ import threading
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "librwmpt.so")
+LIB_PATH = os.environ.get("RWMPT_LIB", os.path.join(_PKG, "librwmpt.so"))  # RWMPT_LIB: A/B-test a variant build
 
 # enums of include/rwmpt.h
 T_ROUGH_CARPET, T_THREE_MIXTURE, T_FULL_ROSENBROCK, T_EVEN_ROSENBROCK, T_HYBRID_ROSENBROCK = 0, 1, 2, 3, 4
@@ -73,6 +73,8 @@ def _declare(lib):
     lib.rwmpt_debug_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.rwmpt_probe_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.rwmpt_probe_peaks.restype = C.c_int
+    lib.rwmpt_probe_issue.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.rwmpt_probe_issue.restype = C.c_int
     lib.rwmpt_run_host.argtypes = [C.POINTER(RunArgs), i32, C.POINTER(u64), C.POINTER(u64)]
     for name in ("rwmpt_rwm_run", "rwmpt_pt_run", "rwmpt_pick_lanes", "rwmpt_log_density", "rwmpt_proposal_sample",
                  "rwmpt_pt_swap", "rwmpt_esjd_reduce", "rwmpt_debug_philox", "rwmpt_run_host"):
@@ -138,4 +140,4 @@ def exported_symbols():
     """Names declared in include/rwmpt.h (used by the CPU test that checks the library exports them all)."""
     return ["rwmpt_version", "rwmpt_last_error", "rwmpt_sizeof_run_args", "rwmpt_rwm_run", "rwmpt_pt_run",
             "rwmpt_count_swap_rounds", "rwmpt_pick_lanes", "rwmpt_log_density", "rwmpt_proposal_sample",
-            "rwmpt_pt_swap", "rwmpt_esjd_reduce", "rwmpt_probe_peaks", "rwmpt_debug_philox", "rwmpt_run_host"]
+            "rwmpt_pt_swap", "rwmpt_esjd_reduce", "rwmpt_probe_peaks", "rwmpt_probe_issue", "rwmpt_debug_philox", "rwmpt_run_host"]

@@ -40,8 +40,13 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ for sm_100a and link librwmpt.so; returns the library path."""
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), tag: str = "") -> str:
+    """Compile every .cu under csrc/ for sm_100a and link librwmpt.so; returns the library path.
+    `defines` / `tag` build an experimental variant (librwmpt_<tag>.so) with extra -D flags."""
+    global OBJ, LIB
+    if tag:
+        OBJ = os.path.join(PKG, "build", tag)
+        LIB = os.path.join(PKG, f"librwmpt_{tag}.so")
     os.makedirs(OBJ, exist_ok=True)
     headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h")) + [__file__]
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
@@ -55,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed for {os.path.basename(src)}:\n{p.stdout}\n{p.stderr}")
@@ -75,5 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    tags = [a[6:] for a in sys.argv if a.startswith("--tag=")]
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, tag=tags[0] if tags else "")
     print(path)

@@ -527,6 +527,51 @@ int rwmpt_probe_peaks(double* fp32_tflops, double* sfu_gops) {
   return RWMPT_OK;
 }
 
+// issue-rate probe at a chosen occupancy: kind 0 = FFMA (8 independent chains), 1 = MUFU.EX2, 2 = Philox rounds
+__global__ void probe_philox_kernel(uint32_t* out, int iters) {
+  uint32_t c0 = threadIdx.x, c1 = blockIdx.x, c2 = 7, c3 = 9, d0 = threadIdx.x * 3, d1 = 1, d2 = 2, d3 = 3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      philox_round(c0, c1, c2, c3, 0x1234567u + r, 0x89abcdefu + r);
+      philox_round(d0, d1, d2, d3, 0x1234567u + r, 0x89abcdefu + r);
+    }
+  }
+  if ((c0 ^ c1 ^ c2 ^ c3 ^ d0 ^ d1 ^ d2 ^ d3) == 0x12345u) out[0] = c0;
+}
+
+int rwmpt_probe_issue(int kind, int blocks, int threads, int iters, double* ops_per_s) {
+  float* d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_out, sizeof(float));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(t0);
+    if (kind == 0) probe_ffma_kernel<<<blocks, threads>>>(d_out, iters);
+    else if (kind == 1) probe_mufu_kernel<<<blocks, threads>>>(d_out, iters);
+    else probe_philox_kernel<<<blocks, threads>>>((uint32_t*)d_out, iters);
+    cudaEventRecord(t1);
+    e = cudaEventSynchronize(t1);
+    if (e != cudaSuccess) break;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    // warp-instructions issued: kinds 0/1: 64 per iteration per thread; kind 2: 16 rounds x 6 instr (2 IMAD.HI, 2 IMAD, 2 LOP3)
+    const double per_iter = kind == 2 ? 96.0 : 64.0;
+    const double winstr = (double)blocks * (threads / 32.0) * iters * per_iter;
+    const double rate = winstr / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(e, "issue probe");
+  if (ops_per_s) *ops_per_s = best;
+  return RWMPT_OK;
+}
+
 int rwmpt_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   uint32_t h[6] = {ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]};
   uint32_t *d_in = nullptr, *d_out = nullptr;

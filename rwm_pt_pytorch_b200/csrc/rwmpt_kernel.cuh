@@ -58,23 +58,45 @@ __host__ __device__ constexpr int pair_words(int E, int PF) {
 // scaling, and the chain's accept uniforms (taken from the leader lane).  Drawing two steps at once uses every
 // Philox word (E=5, Normal: 3 calls per 2 steps) and gives the scheduler three independent Philox chains.
 // PF >= 0: proposal family known at compile time; PF < 0: runtime switch on a.prop_family.
-template <int E, bool IEEE, int PF, class C>
-__device__ __forceinline__ void draw_pair(const KernelArgs& a, const C& c, float (&incA)[E], float (&incB)[E], float& uA,
-                                          float& uB, unsigned long long pair, unsigned long long chain_gid, float scale,
-                                          const float (&dscale)[E]) {
-  constexpr int NW = pair_words(E, PF);
-  constexpr int NC = (NW + 3) / 4;
-  const int pf = PF >= 0 ? PF : a.prop_family;
+// Philox words of one lane for one pair of steps, computed in stages so that the rounds can be spliced between
+// the phases of the Metropolis steps they overlap with (ptxas keeps source order among independent instructions).
+template <int E, int PF>
+struct PairWords {
+  static constexpr int NW = pair_words(E, PF);
+  static constexpr int NC = (NW + 3) / 4;
   uint32_t w[4 * NC];
-  const uint32_t c0 = (uint32_t)pair;
-  const uint32_t c1hi = ((uint32_t)(pair >> 32) << 16) | ((uint32_t)c.sub << 8);
+  template <class C>
+  __device__ __forceinline__ void init(const C& c, unsigned long long pair, unsigned long long chain_gid) {
+    const uint32_t c0 = (uint32_t)pair;
+    const uint32_t c1hi = ((uint32_t)(pair >> 32) << 16) | ((uint32_t)c.sub << 8);
 #pragma unroll
-  for (int k = 0; k < NC; ++k) {
-    const uint4 r = philox_rk(c0, c1hi | (uint32_t)k, (uint32_t)chain_gid, (uint32_t)(chain_gid >> 32), a);
-    w[4 * k + 0] = r.x; w[4 * k + 1] = r.y; w[4 * k + 2] = r.z; w[4 * k + 3] = r.w;
+    for (int k = 0; k < NC; ++k) {
+      w[4 * k + 0] = c0; w[4 * k + 1] = c1hi | (uint32_t)k;
+      w[4 * k + 2] = (uint32_t)chain_gid; w[4 * k + 3] = (uint32_t)(chain_gid >> 32);
+    }
   }
+  template <int R0, int R1>
+  __device__ __forceinline__ void rounds(const KernelArgs& a) {
+#pragma unroll
+    for (int r = R0; r < R1; ++r) {
+#pragma unroll
+      for (int k = 0; k < NC; ++k) philox_round(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3], a.rk[2 * r], a.rk[2 * r + 1]);
+    }
+  }
+};
+
+template <int E, bool IEEE, int PF, class C>
+__device__ __forceinline__ void pair_transform(const KernelArgs& a, const C& c, const uint32_t (&w)[4 * PairWords<E, PF>::NC],
+                                               float (&incA)[E], float (&incB)[E], float& uA, float& uB, float scale,
+                                               const float (&dscale)[E]) {
+  constexpr int NC = PairWords<E, PF>::NC;
+  const int pf = PF >= 0 ? PF : a.prop_family;
   uA = from_leader(u01_from_bits(w[4 * NC - 1]), c);
   uB = from_leader(u01_from_bits(w[4 * NC - 2]), c);
+  if constexpr (!IEEE) {  // fast path compares ln(u) < lar (see mh_accept)
+    uA = lg2_approx(uA) * kLn2;
+    uB = lg2_approx(uB) * kLn2;
+  }
   if (pf == RWMPT_P_LAPLACE) {
     // laplace.py:47-69: u in (-.5,.5); -s * sign(u) * log1p(max(-2|u|, -0.999999))
 #pragma unroll
@@ -123,6 +145,16 @@ __device__ __forceinline__ void draw_pair(const KernelArgs& a, const C& c, float
   }
 }
 
+template <int E, bool IEEE, int PF, class C>
+__device__ __forceinline__ void draw_pair(const KernelArgs& a, const C& c, float (&incA)[E], float (&incB)[E], float& uA,
+                                          float& uB, unsigned long long pair, unsigned long long chain_gid, float scale,
+                                          const float (&dscale)[E]) {
+  PairWords<E, PF> pw;
+  pw.init(c, pair, chain_gid);
+  pw.template rounds<0, 10>(a);
+  pair_transform<E, IEEE, PF>(a, c, pw.w, incA, incB, uA, uB, scale, dscale);
+}
+
 // One uniform per (ladder, sweep, pair) on a separate Philox key.
 __device__ __forceinline__ float swap_uniform(unsigned key0, unsigned key1, unsigned long long ladder_gid,
                                               unsigned long long round, int pair) {
@@ -131,6 +163,14 @@ __device__ __forceinline__ float swap_uniform(unsigned key0, unsigned key1, unsi
   const int q = pair & 3;
   const uint32_t w = q == 0 ? r.x : (q == 1 ? r.y : (q == 2 ? r.z : r.w));
   return u01_from_bits(w);
+}
+
+// Accept rule (rwm_gpu_optimized.py:22-25): (lar > 0) | (u < exp(lar)); NaN compares false -> reject.  In the fast
+// path `u` already holds ln(u) (drawn off the critical path), and for u in [0,1) the rule is exactly ln(u) < lar.
+template <bool IEEE>
+__device__ __forceinline__ bool mh_accept(float lar, float u) {
+  if constexpr (IEEE) return (lar > 0.0f) | (u < expf(lar));  // bitwise: no short-circuit branch
+  else return u < lar;
 }
 
 // pt_rwm_gpu_optimized.py:42-47, literal order; p = min(1, exp(.)), accept iff u < p (:617-621)
@@ -229,7 +269,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     const float lpp = tgt.logp(prop, c);
     // 4. accept rule (rwm_gpu_optimized.py:22-25): NaN compares false -> reject
     const float lar = M::mul(beta, M::sub(lpp, lp));
-    const bool acc = (lar > 0.0f) | (u < M::exp(lar));  // bitwise: no short-circuit branch
+    const bool acc = mh_accept<IEEE>(lar, u);
     // 5. select
     float xo[E];
 #pragma unroll
@@ -349,7 +389,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     for (int e = 0; e < E; ++e) prop[e] = c.ok(e) ? M::add(x[e], inc[e]) : 0.0f;
     const float lpp = tgt.logp(prop, c);
     const float lar = M::mul(beta, M::sub(lpp, lp));
-    const bool acc = (lar > 0.0f) | (u < M::exp(lar));
+    const bool acc = mh_accept<IEEE>(lar, u);
     float j2 = 0.0f;
     if constexpr (IEEE) {
 #pragma unroll
@@ -410,9 +450,37 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       const long long n_fast = (ev - t) >> 1;                  // whole pairs strictly before the event
       for (long long q = 0; q < n_fast; ++q) {
         float nA[E], nB[E], vA, vB;
+#ifndef RWMPT_ORDER
+#define RWMPT_ORDER 0
+#endif
+#if RWMPT_ORDER == 0
         draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
         plain_step(iA, uA, post);
         plain_step(iB, uB, post);
+#elif RWMPT_ORDER == 1
+        plain_step(iA, uA, post);
+        draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
+        plain_step(iB, uB, post);
+#elif RWMPT_ORDER == 2
+        PairWords<E, PF> pw;
+        pw.init(c, pair + 1, chain_gid);
+        pw.template rounds<0, 10>(a);
+        plain_step(iA, uA, post);
+        pair_transform<E, IEEE, PF>(a, c, pw.w, nA, nB, vA, vB, scale, dscale);
+        plain_step(iB, uB, post);
+#elif RWMPT_ORDER == 3
+        PairWords<E, PF> pw;
+        pw.init(c, pair + 1, chain_gid);
+        pw.template rounds<0, 5>(a);
+        plain_step(iA, uA, post);
+        pw.template rounds<5, 10>(a);
+        plain_step(iB, uB, post);
+        pair_transform<E, IEEE, PF>(a, c, pw.w, nA, nB, vA, vB, scale, dscale);
+#elif RWMPT_ORDER == 4
+        plain_step(iA, uA, post);
+        plain_step(iB, uB, post);
+        draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
+#endif
         ++pair;
 #pragma unroll
         for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }

@@ -61,20 +61,24 @@ struct RoughCarpet {
       // work in base 2.  t_k = h xs^2 + b_k xs + c_k (h = -log2(e)/2, b_k = log2(e) m_k, c_k = h m_k^2 + a_k): the
       // quadratic term is common to the three modes, so logsumexp_k t_k = h xs^2 + logsumexp_k (b_k xs + c_k);
       // and sum_i log2(S_i) = log2(prod_i S_i): one lg2 per lane instead of one per coordinate.
-      float hi = 0.0f, prod = 1.0f, q = 0.0f;
+      // The largest of the three terms contributes exactly 2^0 = 1, so only two ex2 are evaluated per coordinate:
+      // S = 1 + 2^(mid - max) + 2^(min - max), mid = (l0 + l1 + l2) - max - min.  Sums / products are combined as
+      // trees (two accumulators) to shorten the dependent chain.
+      float hs[2] = {0.0f, 0.0f}, ps[2] = {1.0f, 1.0f}, qs[2] = {0.0f, 0.0f};
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const float xs = x[e] * s[e];
         const float l0 = fmaf(b0, xs, c0), l1 = fmaf(b1, xs, c1), l2 = fmaf(b2, xs, c2);
         const float mx = fmaxf(fmaxf(l0, l1), l2);
-        const float ss = ex2_approx(l0 - mx) + ex2_approx(l1 - mx) + ex2_approx(l2 - mx);
-        q = fmaf(xs, xs, q);  // padding coordinates hold xs = 0
-        if (c.ok(e)) {
-          hi += mx;
-          prod *= ss;
-        }
+        const float lo = fminf(fminf(l0, l1), l2);
+        const float mid = ((l0 + l1) + l2) - (mx + lo);
+        const float ss = (1.0f + ex2_approx(mid - mx)) + ex2_approx(lo - mx);
+        qs[e & 1] = fmaf(xs, xs, qs[e & 1]);  // padding coordinates hold xs = 0
+        hs[e & 1] += c.ok(e) ? mx : 0.0f;
+        ps[e & 1] *= c.ok(e) ? ss : 1.0f;
       }
-      hi = fmaf(-0.5f * kLog2e, q, hi);
+      const float hi = fmaf(-0.5f * kLog2e, qs[0] + qs[1], hs[0] + hs[1]);
+      const float prod = ps[0] * ps[1];
       const float part = (hi + lg2_approx(prod)) * kLn2;
       return group_sum(part, c) + J;
     }
