@@ -2,6 +2,7 @@
 // launch geometry, family dispatch, and the small stand-alone kernels (proposal sampler, PT swap sweep,
 // ESJD reduction, Philox known-answer hook) plus the host-buffer end-to-end entry.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -99,6 +100,7 @@ static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_
   g->threads = ((g->chains_per_cta * bestW + 31) / 32) * 32;
   g->grid = (n_ladders + ladders_per_cta - 1) / ladders_per_cta;
   g->smem = K > 1 ? (size_t)g->chains_per_cta * (4 + d) * sizeof(float) : 0;
+  g->split = false;
   return RWMPT_OK;
 }
 
@@ -207,7 +209,17 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   a.inj_inc = r->inj_increments; a.inj_u = r->inj_uniforms; a.inj_su = r->inj_swap_uniforms;
   a.decisions = r->decisions; a.swap_dec = r->swap_decisions;
 
-  cudaError_t e = dispatch_mcmc(r->target.family, a, g, ieee, (cudaStream_t)stream);
+  if (const char* sg = getenv("RWMPT_STAGGER")) a.stagger = atoi(sg);
+  cudaError_t e = cudaErrorNotSupported;
+  if (!ieee && !test_mode && 2 * g.threads <= kMaxCtaThreads && getenv("RWMPT_NO_SPLIT") == nullptr) {
+    // warp-specialised variant (producer warps draw the increments): exists for the tuned workloads only
+    LaunchGeom gs = g;
+    gs.split = true;
+    gs.threads = 2 * g.threads;
+    gs.smem = g.smem + (size_t)2 * kSplitPairsPerBatch * 2 * (g.E + 1) * g.threads * sizeof(float);
+    e = dispatch_mcmc(r->target.family, a, gs, ieee, (cudaStream_t)stream);
+  }
+  if (e == cudaErrorNotSupported) e = dispatch_mcmc(r->target.family, a, g, ieee, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "mcmc kernel launch");
   return RWMPT_OK;
 }

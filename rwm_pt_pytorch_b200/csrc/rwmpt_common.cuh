@@ -48,6 +48,7 @@ struct KernelArgs {
   unsigned char* decisions;
   unsigned char* swap_dec;
   long long n_ladders;
+  int stagger;  // experiment: start delay (cycles) for the second wave of CTAs on an SM, to de-phase co-resident warps
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -185,19 +185,42 @@ __device__ __forceinline__ bool swap_accept(float bj, float bk, float lj, float 
 // Template parameters: Target functor; E coordinates per lane; IEEE parity arithmetic; WT lanes per chain (0 = runtime);
 // PF proposal family (-1 = runtime); EXACT: E*W == dim (no padding masks); TEST: injected randomness / decision
 // outputs available.
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
+// SPLIT: warp-specialised variant.  The CTA holds the chains' consumer threads plus an equal number of producer
+// threads; producer lane i draws (Philox + Box-Muller: integer-multiply bound) the increments of consumer lane i into a
+// double-buffered shared-memory ring, PB step-pairs per batch, while the consumers run density / reduce / accept (SFU
+// bound).  Twice the resident warps for the same work, and the two instruction mixes overlap on different pipes.
+constexpr int kSplitPairsPerBatch = 4;
+
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool SPLIT>
 __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a) {
   using M = Mth<IEEE>;
   extern __shared__ float smem[];
+  static_assert(!(SPLIT && TEST), "the warp-specialised variant has no test mode");
 
+  if (a.stagger > 0) {
+    const long long t0 = clock64();
+    const long long wait = (long long)((blockIdx.x / 148) >> 2) * a.stagger;
+    while (clock64() - t0 < wait) {}
+  }
   const int W = WT > 0 ? WT : a.W;
   const int K = a.K, d = a.dim;
-  const int cl = threadIdx.x / W;  // chain within CTA
+  const int nth = SPLIT ? (int)blockDim.x / 2 : (int)blockDim.x;   // consumer threads
+  const bool producer = SPLIT && (int)threadIdx.x >= nth;
+  const int tid = producer ? (int)threadIdx.x - nth : (int)threadIdx.x;
+  auto cta_sync = [&]() {  // barrier among the consumer threads (the whole CTA when not SPLIT)
+    if constexpr (SPLIT) bar_sync_named(1, nth);
+    else __syncthreads();
+  };
+  const int cl = tid / W;  // chain within CTA
   CtxT<WT, EXACT> c;
   c.P = a.P; c.d = d; c.W = W;
-  c.sub = threadIdx.x % W;
+  c.sub = tid % W;
   c.base = c.sub * E;
-  c.lane = threadIdx.x & 31;
+  c.lane = tid & 31;
   c.leader = c.lane & ~(W - 1);
 
   const bool in_cta = cl < a.chains_per_cta;
@@ -224,6 +247,37 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
   const float beta = a.beta[chain];
   const float scale = a.prop_scale ? a.prop_scale[chain] : 1.0f;
 
+  // ---- SPLIT ring: [2 buffers][PB pairs][2 halves][E + 1][nth] floats after the swap region -------------------
+  const long long s_first = a.step_offset + 1;
+  const unsigned long long pair0 = (unsigned long long)(s_first - 1) >> 1;
+  const unsigned long long pair_last = (unsigned long long)(a.step_offset + a.n_steps - 1) >> 1;
+  const long long n_pairs = a.n_steps > 0 ? (long long)(pair_last - pair0) + 1 : 0;
+  const long long n_batches = (n_pairs + kSplitPairsPerBatch - 1) / kSplitPairsPerBatch;
+  float* ring = smem + (K > 1 ? a.chains_per_cta * (4 + d) : 0);
+  const int half_stride = (E + 1) * nth;
+  const int buf_stride = kSplitPairsPerBatch * 2 * half_stride;
+  if constexpr (SPLIT) {
+    if (producer) {
+      for (long long b = 0; b < n_batches; ++b) {
+        float* buf = ring + (b & 1) * buf_stride;
+#pragma unroll 1
+        for (int q = 0; q < kSplitPairsPerBatch; ++q) {
+          const unsigned long long p = pair0 + (unsigned long long)(b * kSplitPairsPerBatch + q);
+          if (p > pair_last) break;
+          float iA[E], iB[E], uA, uB;
+          draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, p, chain_gid, scale, dscale);
+          float* dst = buf + q * 2 * half_stride + tid;
+#pragma unroll
+          for (int e = 0; e < E; ++e) { dst[e * nth] = iA[e]; dst[half_stride + e * nth] = iB[e]; }
+          dst[E * nth] = uA;
+          dst[half_stride + E * nth] = uB;
+        }
+        bar_sync_named(0, 2 * nth);  // batch b is ready (and the consumers are done with batch b-1)
+      }
+      return;
+    }
+  }
+
   // shared memory carve-up for the swap sweep
   float* s_lp = smem;                                  // [chains_per_cta]
   int* s_src = (int*)(smem + a.chains_per_cta);        // [chains_per_cta]
@@ -232,11 +286,10 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
   float* s_x = s_beta + a.chains_per_cta;              // [chains_per_cta, d]
   if (K > 1) {
     if (in_cta && c.sub == 0) s_beta[cl] = beta;
-    __syncthreads();
+    cta_sync();
   }
 
   // countdowns (no per-step modulo)
-  const long long s_first = a.step_offset + 1;
   long long swap_cd = -1;
   if (K > 1) {
     long long nxt = ((s_first + a.swap_every - 1) / a.swap_every) * a.swap_every;
@@ -294,7 +347,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
             if (c.base + e < d) s_x[cl * d + c.base + e] = x[e];
           if (c.sub == 0) { s_lp[cl] = lp; s_src[cl] = cl; s_ok[cl] = 0; }
         }
-        __syncthreads();
+        cta_sync();
         const unsigned long long round_g = (unsigned long long)(a.rounds_before + round_local);  // 0-based
         const long long su_base = (round_local * a.n_ladders + ladder) * (K - 1);
         const bool inj_su = TEST && a.inj_su != nullptr;
@@ -325,7 +378,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
               if (TEST && a.swap_dec) a.swap_dec[su_base + j] = ok ? 1 : 0;
             }
           }
-          __syncthreads();
+          cta_sync();
           if (valid) {
             const int src = s_src[cl];
             if (src != cl) {
@@ -338,7 +391,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
           }
         }
         round_local++;
-        __syncthreads();  // s_x / s_lp are rewritten at the next sweep
+        cta_sync();  // s_x / s_lp are rewritten at the next sweep
       }
       swap_cd--;
     }
@@ -423,6 +476,47 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
           inc[e] = (i < d) ? a.inj_inc[(t * a.n_chains + chain) * d + i] : 0.0f;
         }
         do_step(inc, a.inj_u[t * a.n_chains + chain], t);
+      }
+    }
+  } else if (SPLIT) {
+    if constexpr (SPLIT) {
+      const long long h0 = (s_first - 1) & 1;  // the run may start on the second step of a pair
+      long long t = 0, ev = -1;
+      auto next_event = [&]() {
+        long long v = t | 63;
+        if (a.n_steps - 1 < v) v = a.n_steps - 1;
+        if (t < burn_t && burn_t - 1 < v) v = burn_t - 1;
+        if (K > 1 && t + swap_cd < v) v = t + swap_cd;
+        if (a.samples != nullptr && t + store_cd < v) v = t + store_cd;
+        return v;
+      };
+      ev = next_event();
+      for (long long b = 0; b < n_batches; ++b) {
+        bar_sync_named(0, 2 * nth);  // batch b has been produced
+        const float* buf = ring + (b & 1) * buf_stride;
+#pragma unroll 1
+        for (int q = 0; q < kSplitPairsPerBatch; ++q) {
+          const long long pl = b * kSplitPairsPerBatch + q;
+          if (pl >= n_pairs) break;
+          const float* src = buf + q * 2 * half_stride + tid;
+          float iA[E], iB[E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) { iA[e] = src[e * nth]; iB[e] = src[half_stride + e * nth]; }
+          const float uA = src[E * nth], uB = src[half_stride + E * nth];
+          const long long tA = 2 * pl - h0, tB = tA + 1;
+          if (tA == t && tB < ev) {  // no event inside this pair: two branch-free steps
+            const bool post = t >= burn_t;
+            plain_step(iA, uA, post);
+            plain_step(iB, uB, post);
+            t += 2;
+            if (K > 1) swap_cd -= 2;
+            if (a.samples != nullptr) store_cd -= 2;
+          } else {
+            if (tA == t && t < a.n_steps) { do_step(iA, uA, t); ++t; }
+            if (tB == t && t < a.n_steps) { do_step(iB, uB, t); ++t; }
+            ev = next_event();
+          }
+        }
       }
     }
   } else if (a.n_steps > 0) {
@@ -558,6 +652,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) logp_kernel(const float* __res
 struct LaunchGeom {
   int E;
   int W;
+  bool split;  // warp-specialised variant: threads = 2 x consumer threads, smem includes the increment ring
   int threads;
   int chains_per_cta;
   long long grid;
