@@ -34,10 +34,10 @@ if ROOT not in sys.path:
 # algorithmic work per chain-step: F fp32 flops, S transcendentals, stored bytes
 WORKLOADS = {
     "c3": dict(desc="C3 PT-RWM RoughCarpet d=20 K=8 swap_every=10 Normal var=0.9, 1024 ladders/GPU, accumulators only",
-               kind="pt", target="rough_carpet", dim=20, K=8, units=1024, T=100_000, burn_in=2000, swap_every=10,
+               kind="pt", target="rough_carpet", dim=20, K=8, units=1024, T=500_000, burn_in=2000, swap_every=10,
                var=0.9, F=644, S=121, bytes=0),
     "c2": dict(desc="C2 RWM EvenRosenbrock d=20 Normal var=0.297436^2/20, 4096 chains/GPU, accumulators only",
-               kind="rwm", target="even_rosenbrock", dim=20, K=1, units=4096, T=200_000, burn_in=1000, swap_every=1,
+               kind="rwm", target="even_rosenbrock", dim=20, K=1, units=4096, T=1_000_000, burn_in=1000, swap_every=1,
                var=0.297436 ** 2 / 20, F=294, S=41, bytes=0),
     "c4": dict(desc="C4 PT-RWM ThreeMixture d=50 (+-15) K=8 Laplace var_i=2.38^2/50, 512 ladders/GPU, all chains stored",
                kind="pt", target="three_mixture", dim=50, K=8, units=512, T=2_000, burn_in=0, swap_every=10,

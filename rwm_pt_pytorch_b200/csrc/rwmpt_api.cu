@@ -211,8 +211,9 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
 
   if (const char* sg = getenv("RWMPT_STAGGER")) a.stagger = atoi(sg);
   cudaError_t e = cudaErrorNotSupported;
-  if (!ieee && !test_mode && 2 * g.threads <= kMaxCtaThreads && getenv("RWMPT_NO_SPLIT") == nullptr) {
-    // warp-specialised variant (producer warps draw the increments): exists for the tuned workloads only
+  if (!ieee && !test_mode && 2 * g.threads <= kMaxCtaThreads && getenv("RWMPT_SPLIT") != nullptr) {
+    // warp-specialised variant (producer warps draw the increments): opt-in experiment, measured slower than the
+    // single-role kernel on B200 (profiles/README.md); exists for the tuned workloads only
     LaunchGeom gs = g;
     gs.split = true;
     gs.threads = 2 * g.threads;
