@@ -260,6 +260,7 @@ def main():
     import torch
     import torch.distributed as dist
     from rwm_pt_pytorch_b200 import _lib
+    from rwm_pt_pytorch_b200 import distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -283,7 +284,7 @@ def main():
         if store != "none":
             batch.allocate_storage(store, T * (args.steps + args.warmup) + 2, 1, with_logp=True)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-        stats = torch.zeros(4, dtype=torch.float64, device=dev)
+        reduced = None
         for _ in range(args.warmup):
             batch.run(T)
         torch.cuda.synchronize()
@@ -302,8 +303,7 @@ def main():
             batch.run(T)                                                  # ONE launch of the fused kernel
             launches += 1
             if world > 1:                                                 # the path's only collective: accumulators
-                stats[0] = batch.accept_count.sum(); stats[1] = batch.sq_jump_sum.sum(); stats[2] = batch.swap_accepts.sum()
-                dist.all_reduce(stats)
+                reduced = D.allreduce_statistics(D.local_statistics(algo), device=dev)
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
@@ -319,7 +319,8 @@ def main():
         ms_per_step = ms / args.steps
         rate = world * nc * T / (ms_per_step * 1e-3)
         algo._refresh_stats()
-        return dict(rate=rate, ms_per_step=ms_per_step, launches=launches, clocks=clocks, algo=algo, batch=batch, t=t)
+        return dict(rate=rate, ms_per_step=ms_per_step, launches=launches, clocks=clocks, algo=algo, batch=batch, t=t,
+                    reduced=reduced)
 
     m = measure(wl, store, True)
     algo, batch = m["algo"], m["batch"]
@@ -367,6 +368,8 @@ def main():
         "esjd": esjd, "esjd_per_sec": None if esjd is None else esjd * m["rate"] / wl["K"],
         "acceptance_rate": float(batch.accept_count.sum().item()) / max(post * batch.n_chains, 1),
     }
+    if m["reduced"] is not None:
+        line["all_ranks"] = D.pooled_summary(m["reduced"], m["reduced"]["chain_steps"] / wl["K"])
     if wl["kind"] == "pt":
         line["swap_acceptance_rate"] = algo.swap_acceptance_rate
         line["ladder_steps_per_sec"] = m["rate"] / wl["K"]

@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing for the sampling path: one process per GPU (`torch.distributed`, NCCL on GPUs, gloo in the CPU
+tests).  Chains (RWM) and whole ladders (PT) are independent, so the path shards with NO data-path collective: every
+rank runs a contiguous block of units with `chain_id_base` set so that the Philox subsequence of a chain is its GLOBAL
+id -- results are identical for 1, 2, 4 or 8 GPUs.  Collectives happen once, after the run: a SUM all-reduce of the fp64
+accumulators and an (optional) gather of retained samples."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+STAT_KEYS = ("accept_count", "chain_steps", "sq_jump_sum", "swap_attempts", "swap_accepts", "sq_beta_jump_sum")
+
+
+def shard_range(n_units: int, rank: int, world: int) -> Tuple[int, int]:
+    """(first unit, number of units) of `rank`: contiguous blocks, the remainder spread over the first ranks."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(int(n_units), world)
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+def chain_id_base(first_unit: int, n_temps: int = 1) -> int:
+    """Global id of the first chain of a shard (ladders own n_temps consecutive chain ids)."""
+    return int(first_unit) * int(n_temps)
+
+
+def local_statistics(algo) -> Dict[str, float]:
+    """fp64 accumulators of one rank's sampler (RandomWalkMH_GPU_Optimized / ParallelTemperingRWM_GPU_Optimized)."""
+    b = algo._batch
+    post = b.post_burn_in_steps()
+    out = dict.fromkeys(STAT_KEYS, 0.0)
+    out["accept_count"] = float(b.accept_count.sum().item())
+    out["chain_steps"] = float(post * b.n_chains)
+    if b.K == 1:
+        out["sq_jump_sum"] = float(b.sq_jump_sum.sum().item())
+    else:
+        out["sq_jump_sum"] = float(b.sq_jump_sum.view(b.L, b.K)[:, 0].sum().item())   # cold chains
+        out["swap_attempts"] = float(b.swap_rounds() * (b.K - 1) * b.L)
+        acc = b.swap_accepts[:, : b.K - 1].to(torch.float64)
+        out["swap_accepts"] = float(acc.sum().item())
+        betas = b.beta.view(b.L, b.K)[0].to(torch.float64)
+        out["sq_beta_jump_sum"] = float((acc.sum(dim=0) * (betas[:-1] - betas[1:]) ** 2).sum().item())
+    return out
+
+
+def allreduce_statistics(stats: Dict[str, float], device=None, group=None) -> Dict[str, float]:
+    """SUM all-reduce of the accumulators over all ranks (the path's only collective besides the sample gather)."""
+    t = torch.tensor([float(stats.get(k, 0.0)) for k in STAT_KEYS], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return {k: float(v) for k, v in zip(STAT_KEYS, t.tolist())}
+
+
+def pooled_summary(total: Dict[str, float], n_cold_chain_steps: Optional[float] = None) -> Dict[str, float]:
+    """Job-level rates from reduced accumulators."""
+    steps = max(total["chain_steps"], 1.0)
+    cold_steps = n_cold_chain_steps if n_cold_chain_steps else steps
+    out = {"acceptance_rate": total["accept_count"] / steps, "esjd": total["sq_jump_sum"] / max(cold_steps, 1.0)}
+    if total["swap_attempts"] > 0:
+        out["swap_acceptance_rate"] = total["swap_accepts"] / total["swap_attempts"]
+        out["pt_esjd"] = total["sq_beta_jump_sum"] / total["swap_attempts"]
+    return out
+
+
+def gather_samples(local: torch.Tensor, counts, dst: Optional[int] = None, group=None):
+    """Gather per-rank sample blocks (units, rows, dim) in global unit order.  `counts[r]` = units of rank r (shards may be
+    uneven, so blocks are padded to the largest).  dst=None -> every rank gets the result (all_gather); else only `dst`."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mx = max(counts)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    if dst is None:
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+    else:
+        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+        dist.gather(pad, bufs, dst=dst, group=group)
+        if rank != dst:
+            return None
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
