@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--T", type=int, default=0, help="Metropolis steps per launch (0 = workload default)")
     ap.add_argument("--units", type=int, default=0, help="ladders / chains per GPU (0 = workload default)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per chain (0 = auto)")
+    ap.add_argument("--store", default="", choices=["", "none", "cold", "all"], help="override the workload's trajectory storage")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--also", default="", help="comma list of extra workloads reported under 'also' (rank 0, N=1)")
@@ -276,7 +277,9 @@ def main():
         wl["T"] = args.T
     if args.units:
         wl["units"] = args.units
-    store = wl.get("store", "none")
+    store = args.store or wl.get("store", "none")
+    if store != "none" and "store" not in wl:
+        wl["bytes"] = 4 * wl["dim"] + 4 if store == "all" else (4 * wl["dim"] + 4) / wl["K"]
 
     def measure(wl, store, with_clocks):
         algo, batch, t = build_sampler(wl, dev, rank, store, args.lanes)

@@ -15,7 +15,7 @@ import subprocess
 import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-CSRC = os.path.join(PKG, "csrc")
+CSRC = os.environ.get("RWMPT_CSRC", os.path.join(PKG, "csrc"))  # RWMPT_CSRC: build an alternative source tree (A/B tests)
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "librwmpt.so")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")

@@ -305,6 +305,52 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     store_m = (nxt - a.store_start) / a.thin - 1;
   }
   const long long store_chain = a.store_mode == RWMPT_STORE_ALL ? chain : ladder;
+  // Retained samples are staged in shared memory, S = a.stage_rows rows per chain, and flushed as contiguous
+  // S*d-float blocks (layout (chain, row, dim): the S rows of one chain are adjacent in HBM) with vector stores of
+  // a.stage_vw floats (float4 when d % 4 == 0, float2 when d is even): one warp instruction writes 512 contiguous bytes.
+  const int S = a.stage_rows;
+  const int st_stride = (S * d + 3) & ~3;
+  float* st_base = smem + a.stage_off;                                  // [chains_per_cta][st_stride]
+  float* st_lp_base = st_base + (size_t)a.chains_per_cta * st_stride;    // [chains_per_cta][S]
+  float* st_x = st_base + (in_cta ? cl : 0) * st_stride;
+  const bool stage_me = storing && valid;
+  const bool store_each = a.samples != nullptr && a.thin == 1 && s_first > a.store_start;  // every step of this run is retained
+  int nbuf = 0;
+  long long m_base = store_m;   // row index of staged row 0
+  auto stage_flush = [&]() {
+    // Each chain's W lanes copy their own chain's staged block: consecutive lanes write consecutive vectors, so every
+    // 32-byte sector is written whole exactly once; no CTA barrier (a staging region is only touched by its own warp).
+    __syncwarp();
+    long long rows = a.sample_rows - m_base;
+    if (rows > nbuf) rows = nbuf;
+    if (rows > 0 && stage_me) {
+      const int n = (int)rows * d;
+      const float* src = st_x;
+      float* dst = a.samples + (store_chain * a.sample_stride + m_base) * d;
+      if (a.stage_vw == 4) {
+        for (int v = c.sub; v < (n >> 2); v += W) reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(src)[v];
+      } else if (a.stage_vw == 2) {
+        for (int v = c.sub; v < (n >> 1); v += W) reinterpret_cast<float2*>(dst)[v] = reinterpret_cast<const float2*>(src)[v];
+      } else {
+        for (int v = c.sub; v < n; v += W) dst[v] = src[v];
+      }
+      if (a.sample_logp != nullptr)
+        for (int r = c.sub; r < (int)rows; r += W) a.sample_logp[store_chain * a.sample_stride + m_base + r] = st_lp_base[(size_t)cl * S + r];
+    }
+    __syncwarp();
+    m_base += nbuf;
+    nbuf = 0;
+  };
+  auto stage_row = [&](const float (&xs)[E], float lpv) {
+    if (stage_me) {
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (c.ok(e)) st_x[nbuf * d + c.base + e] = xs[e];
+      if (c.sub == 0) st_lp_base[(size_t)cl * S + nbuf] = lpv;
+    }
+    ++nbuf;
+    if (nbuf == S) stage_flush();
+  };
   const long long burn_t = a.burn_in > a.step_offset ? a.burn_in - a.step_offset : 0;  // local steps t >= burn_t count
 
   unsigned long long n_acc = 0, n_swap_acc = 0, last_attempt = 0;
@@ -419,18 +465,16 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
 
     // 8. retained samples: layout (chain, row, dim)
     if (a.samples != nullptr) {
-      if (store_cd == 0) {
-        store_cd = a.thin;
-        if (storing && valid && store_m < a.sample_rows) {
-          float* dst = a.samples + (store_chain * a.sample_stride + store_m) * d;
-#pragma unroll
-          for (int e = 0; e < E; ++e)
-            if (c.base + e < d) dst[c.base + e] = x[e];
-          if (a.sample_logp && c.sub == 0) a.sample_logp[store_chain * a.sample_stride + store_m] = lp;
+      if (store_each) {
+        stage_row(x, lp);
+      } else {
+        if (store_cd == 0) {
+          store_cd = a.thin;
+          stage_row(x, lp);
+          store_m++;
         }
-        store_m++;
+        store_cd--;
       }
-      store_cd--;
     }
   };
 
@@ -463,6 +507,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     }
     lp = acc ? lpp : lp;
     n_acc32 += (post & acc) ? 1u : 0u;
+    if (store_each) stage_row(x, lp);
   };
 
   const bool inject = TEST && a.inj_inc != nullptr;
@@ -487,7 +532,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
         if (a.n_steps - 1 < v) v = a.n_steps - 1;
         if (t < burn_t && burn_t - 1 < v) v = burn_t - 1;
         if (K > 1 && t + swap_cd < v) v = t + swap_cd;
-        if (a.samples != nullptr && t + store_cd < v) v = t + store_cd;
+        if (a.samples != nullptr && !store_each && t + store_cd < v) v = t + store_cd;
         return v;
       };
       ev = next_event();
@@ -539,7 +584,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       if (a.n_steps - 1 < ev) ev = a.n_steps - 1;              // last step (also covers an odd tail)
       if (t < burn_t && burn_t - 1 < ev) ev = burn_t - 1;      // burn-in boundary inside a pair
       if (K > 1 && t + swap_cd < ev) ev = t + swap_cd;         // sweep due after that step
-      if (a.samples != nullptr && t + store_cd < ev) ev = t + store_cd;
+      if (a.samples != nullptr && !store_each && t + store_cd < ev) ev = t + store_cd;
       const bool post = t >= burn_t;
       const long long n_fast = (ev - t) >> 1;                  // whole pairs strictly before the event
       for (long long q = 0; q < n_fast; ++q) {
@@ -601,7 +646,8 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     }
   }
 
-  // epilogue: state, log-density, accumulators
+  // epilogue: staged samples, state, log-density, accumulators
+  if (a.samples != nullptr && nbuf > 0) stage_flush();
   jump_d += (double)jump_f;
   n_acc += n_acc32;
   jump_d = group_sum_f64_w<WT>(jump_d, W);
