@@ -100,7 +100,6 @@ static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_
   g->threads = ((g->chains_per_cta * bestW + 31) / 32) * 32;
   g->grid = (n_ladders + ladders_per_cta - 1) / ladders_per_cta;
   g->smem = K > 1 ? (size_t)g->chains_per_cta * (4 + d) * sizeof(float) : 0;
-  g->split = false;
   return RWMPT_OK;
 }
 
@@ -209,7 +208,6 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   a.inj_inc = r->inj_increments; a.inj_u = r->inj_uniforms; a.inj_su = r->inj_swap_uniforms;
   a.decisions = r->decisions; a.swap_dec = r->swap_decisions;
 
-  if (const char* sg = getenv("RWMPT_STAGGER")) a.stagger = atoi(sg);
   if (r->samples) {
     // staging region after the swap region: S rows per chain, S = 8 unless that needs more than ~64 KiB per CTA
     const size_t swap_floats = (g.smem / sizeof(float) + 3) & ~(size_t)3;
@@ -223,17 +221,7 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
     a.stage_vw = (d % 4 == 0 && p % 16 == 0) ? 4 : ((d % 2 == 0 && p % 8 == 0) ? 2 : 1);
     g.smem = (swap_floats + (size_t)g.chains_per_cta * st_stride + lp_floats) * sizeof(float);
   }
-  cudaError_t e = cudaErrorNotSupported;
-  if (!ieee && !test_mode && !r->samples && 2 * g.threads <= kMaxCtaThreads && getenv("RWMPT_SPLIT") != nullptr) {
-    // warp-specialised variant (producer warps draw the increments): opt-in experiment, measured slower than the
-    // single-role kernel on B200 (profiles/README.md); exists for the tuned workloads only
-    LaunchGeom gs = g;
-    gs.split = true;
-    gs.threads = 2 * g.threads;
-    gs.smem = g.smem + (size_t)2 * kSplitPairsPerBatch * 2 * (g.E + 1) * g.threads * sizeof(float);
-    e = dispatch_mcmc(r->target.family, a, gs, ieee, (cudaStream_t)stream);
-  }
-  if (e == cudaErrorNotSupported) e = dispatch_mcmc(r->target.family, a, g, ieee, (cudaStream_t)stream);
+  cudaError_t e = dispatch_mcmc(r->target.family, a, g, ieee, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "mcmc kernel launch");
   return RWMPT_OK;
 }

@@ -51,7 +51,6 @@ struct KernelArgs {
   int stage_rows;  // rows per chain staged in shared memory before a coalesced flush
   int stage_off;   // offset (floats) of the staging region in dynamic shared memory
   int stage_vw;    // floats per vector store of the flush (4, 2 or 1)
-  int stagger;  // experiment: start delay (cycles) for the second wave of CTAs on an SM, to de-phase co-resident warps
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -17,6 +17,8 @@
 // (pt_rwm_gpu_optimized.py:541-574, 61-84, 594-633, 635-653), and the proposal plugins' samplers.
 #pragma once
 
+#include <type_traits>
+
 #include "rwmpt_common.cuh"
 #include "rwmpt_targets.cuh"
 
@@ -185,36 +187,15 @@ __device__ __forceinline__ bool swap_accept(float bj, float bk, float lj, float 
 // Template parameters: Target functor; E coordinates per lane; IEEE parity arithmetic; WT lanes per chain (0 = runtime);
 // PF proposal family (-1 = runtime); EXACT: E*W == dim (no padding masks); TEST: injected randomness / decision
 // outputs available.
-// SPLIT: warp-specialised variant.  The CTA holds the chains' consumer threads plus an equal number of producer
-// threads; producer lane i draws (Philox + Box-Muller: integer-multiply bound) the increments of consumer lane i into a
-// double-buffered shared-memory ring, PB step-pairs per batch, while the consumers run density / reduce / accept (SFU
-// bound).  Twice the resident warps for the same work, and the two instruction mixes overlap on different pipes.
-constexpr int kSplitPairsPerBatch = 4;
-
-__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool SPLIT>
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
 __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a) {
   using M = Mth<IEEE>;
   extern __shared__ float smem[];
-  static_assert(!(SPLIT && TEST), "the warp-specialised variant has no test mode");
 
-  if (a.stagger > 0) {
-    const long long t0 = clock64();
-    const long long wait = (long long)((blockIdx.x / 148) >> 2) * a.stagger;
-    while (clock64() - t0 < wait) {}
-  }
   const int W = WT > 0 ? WT : a.W;
   const int K = a.K, d = a.dim;
-  const int nth = SPLIT ? (int)blockDim.x / 2 : (int)blockDim.x;   // consumer threads
-  const bool producer = SPLIT && (int)threadIdx.x >= nth;
-  const int tid = producer ? (int)threadIdx.x - nth : (int)threadIdx.x;
-  auto cta_sync = [&]() {  // barrier among the consumer threads (the whole CTA when not SPLIT)
-    if constexpr (SPLIT) bar_sync_named(1, nth);
-    else __syncthreads();
-  };
+  const int tid = (int)threadIdx.x;
+  auto cta_sync = [&]() { __syncthreads(); };
   const int cl = tid / W;  // chain within CTA
   CtxT<WT, EXACT> c;
   c.P = a.P; c.d = d; c.W = W;
@@ -247,37 +228,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
   const float beta = a.beta[chain];
   const float scale = a.prop_scale ? a.prop_scale[chain] : 1.0f;
 
-  // ---- SPLIT ring: [2 buffers][PB pairs][2 halves][E + 1][nth] floats after the swap region -------------------
   const long long s_first = a.step_offset + 1;
-  const unsigned long long pair0 = (unsigned long long)(s_first - 1) >> 1;
-  const unsigned long long pair_last = (unsigned long long)(a.step_offset + a.n_steps - 1) >> 1;
-  const long long n_pairs = a.n_steps > 0 ? (long long)(pair_last - pair0) + 1 : 0;
-  const long long n_batches = (n_pairs + kSplitPairsPerBatch - 1) / kSplitPairsPerBatch;
-  float* ring = smem + (K > 1 ? a.chains_per_cta * (4 + d) : 0);
-  const int half_stride = (E + 1) * nth;
-  const int buf_stride = kSplitPairsPerBatch * 2 * half_stride;
-  if constexpr (SPLIT) {
-    if (producer) {
-      for (long long b = 0; b < n_batches; ++b) {
-        float* buf = ring + (b & 1) * buf_stride;
-#pragma unroll 1
-        for (int q = 0; q < kSplitPairsPerBatch; ++q) {
-          const unsigned long long p = pair0 + (unsigned long long)(b * kSplitPairsPerBatch + q);
-          if (p > pair_last) break;
-          float iA[E], iB[E], uA, uB;
-          draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, p, chain_gid, scale, dscale);
-          float* dst = buf + q * 2 * half_stride + tid;
-#pragma unroll
-          for (int e = 0; e < E; ++e) { dst[e * nth] = iA[e]; dst[half_stride + e * nth] = iB[e]; }
-          dst[E * nth] = uA;
-          dst[half_stride + E * nth] = uB;
-        }
-        bar_sync_named(0, 2 * nth);  // batch b is ready (and the consumers are done with batch b-1)
-      }
-      return;
-    }
-  }
-
   // shared memory carve-up for the swap sweep
   float* s_lp = smem;                                  // [chains_per_cta]
   int* s_src = (int*)(smem + a.chains_per_cta);        // [chains_per_cta]
@@ -480,7 +431,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
 
   // ---- plain step: no sweep, no retained sample, no flush -- a single basic block, so that ptxas can interleave it
   // with the Philox / Box-Muller stream of the next pair of steps.  `post` is invariant between events.
-  auto plain_step = [&](const float (&inc)[E], const float u, const bool post) {
+  auto plain_step = [&](const float (&inc)[E], const float u, const bool post, auto store_tag) {
     float prop[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) prop[e] = c.ok(e) ? M::add(x[e], inc[e]) : 0.0f;
@@ -507,7 +458,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     }
     lp = acc ? lpp : lp;
     n_acc32 += (post & acc) ? 1u : 0u;
-    if (store_each) stage_row(x, lp);
+    if constexpr (decltype(store_tag)::value) stage_row(x, lp);
   };
 
   const bool inject = TEST && a.inj_inc != nullptr;
@@ -521,47 +472,6 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
           inc[e] = (i < d) ? a.inj_inc[(t * a.n_chains + chain) * d + i] : 0.0f;
         }
         do_step(inc, a.inj_u[t * a.n_chains + chain], t);
-      }
-    }
-  } else if (SPLIT) {
-    if constexpr (SPLIT) {
-      const long long h0 = (s_first - 1) & 1;  // the run may start on the second step of a pair
-      long long t = 0, ev = -1;
-      auto next_event = [&]() {
-        long long v = t | 63;
-        if (a.n_steps - 1 < v) v = a.n_steps - 1;
-        if (t < burn_t && burn_t - 1 < v) v = burn_t - 1;
-        if (K > 1 && t + swap_cd < v) v = t + swap_cd;
-        if (a.samples != nullptr && !store_each && t + store_cd < v) v = t + store_cd;
-        return v;
-      };
-      ev = next_event();
-      for (long long b = 0; b < n_batches; ++b) {
-        bar_sync_named(0, 2 * nth);  // batch b has been produced
-        const float* buf = ring + (b & 1) * buf_stride;
-#pragma unroll 1
-        for (int q = 0; q < kSplitPairsPerBatch; ++q) {
-          const long long pl = b * kSplitPairsPerBatch + q;
-          if (pl >= n_pairs) break;
-          const float* src = buf + q * 2 * half_stride + tid;
-          float iA[E], iB[E];
-#pragma unroll
-          for (int e = 0; e < E; ++e) { iA[e] = src[e * nth]; iB[e] = src[half_stride + e * nth]; }
-          const float uA = src[E * nth], uB = src[half_stride + E * nth];
-          const long long tA = 2 * pl - h0, tB = tA + 1;
-          if (tA == t && tB < ev) {  // no event inside this pair: two branch-free steps
-            const bool post = t >= burn_t;
-            plain_step(iA, uA, post);
-            plain_step(iB, uB, post);
-            t += 2;
-            if (K > 1) swap_cd -= 2;
-            if (a.samples != nullptr) store_cd -= 2;
-          } else {
-            if (tA == t && t < a.n_steps) { do_step(iA, uA, t); ++t; }
-            if (tB == t && t < a.n_steps) { do_step(iB, uB, t); ++t; }
-            ev = next_event();
-          }
-        }
       }
     }
   } else if (a.n_steps > 0) {
@@ -587,44 +497,49 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       if (a.samples != nullptr && !store_each && t + store_cd < ev) ev = t + store_cd;
       const bool post = t >= burn_t;
       const long long n_fast = (ev - t) >> 1;                  // whole pairs strictly before the event
+      auto fast_pairs = [&](auto store_tag) {
       for (long long q = 0; q < n_fast; ++q) {
-        float nA[E], nB[E], vA, vB;
-#ifndef RWMPT_ORDER
-#define RWMPT_ORDER 0
-#endif
-#if RWMPT_ORDER == 0
-        draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
-        plain_step(iA, uA, post);
-        plain_step(iB, uB, post);
-#elif RWMPT_ORDER == 1
-        plain_step(iA, uA, post);
-        draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
-        plain_step(iB, uB, post);
-#elif RWMPT_ORDER == 2
-        PairWords<E, PF> pw;
-        pw.init(c, pair + 1, chain_gid);
-        pw.template rounds<0, 10>(a);
-        plain_step(iA, uA, post);
-        pair_transform<E, IEEE, PF>(a, c, pw.w, nA, nB, vA, vB, scale, dscale);
-        plain_step(iB, uB, post);
-#elif RWMPT_ORDER == 3
-        PairWords<E, PF> pw;
-        pw.init(c, pair + 1, chain_gid);
-        pw.template rounds<0, 5>(a);
-        plain_step(iA, uA, post);
-        pw.template rounds<5, 10>(a);
-        plain_step(iB, uB, post);
-        pair_transform<E, IEEE, PF>(a, c, pw.w, nA, nB, vA, vB, scale, dscale);
-#elif RWMPT_ORDER == 4
-        plain_step(iA, uA, post);
-        plain_step(iB, uB, post);
-        draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
-#endif
-        ++pair;
-#pragma unroll
-        for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
-        uA = vA; uB = vB;
-      }
+          float nA[E], nB[E], vA, vB;
+  #ifndef RWMPT_ORDER
+  #define RWMPT_ORDER 0
+  #endif
+  #if RWMPT_ORDER == 0
+          draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
+          plain_step(iA, uA, post, store_tag);
+          plain_step(iB, uB, post, store_tag);
+  #elif RWMPT_ORDER == 1
+          plain_step(iA, uA, post, store_tag);
+          draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
+          plain_step(iB, uB, post, store_tag);
+  #elif RWMPT_ORDER == 2
+          PairWords<E, PF> pw;
+          pw.init(c, pair + 1, chain_gid);
+          pw.template rounds<0, 10>(a);
+          plain_step(iA, uA, post, store_tag);
+          pair_transform<E, IEEE, PF>(a, c, pw.w, nA, nB, vA, vB, scale, dscale);
+          plain_step(iB, uB, post, store_tag);
+  #elif RWMPT_ORDER == 3
+          PairWords<E, PF> pw;
+          pw.init(c, pair + 1, chain_gid);
+          pw.template rounds<0, 5>(a);
+          plain_step(iA, uA, post, store_tag);
+          pw.template rounds<5, 10>(a);
+          plain_step(iB, uB, post, store_tag);
+          pair_transform<E, IEEE, PF>(a, c, pw.w, nA, nB, vA, vB, scale, dscale);
+  #elif RWMPT_ORDER == 4
+          plain_step(iA, uA, post, store_tag);
+          plain_step(iB, uB, post, store_tag);
+          draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
+  #endif
+          ++pair;
+  #pragma unroll
+          for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
+          uA = vA; uB = vB;
+        }
+      };
+      // the retained-sample variant is a separate instantiation so that the accumulators-only loop stays one basic block
+      if (store_each) fast_pairs(std::true_type{});
+      else fast_pairs(std::false_type{});
       t += 2 * n_fast;
       if (K > 1) swap_cd -= 2 * n_fast;
       if (a.samples != nullptr) store_cd -= 2 * n_fast;
@@ -698,7 +613,6 @@ __global__ void __launch_bounds__(kMaxCtaThreads) logp_kernel(const float* __res
 struct LaunchGeom {
   int E;
   int W;
-  bool split;  // warp-specialised variant: threads = 2 x consumer threads, smem includes the increment ring
   int threads;
   int chains_per_cta;
   long long grid;

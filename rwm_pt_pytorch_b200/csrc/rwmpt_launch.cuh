@@ -10,9 +10,9 @@ namespace rwmpt {
 #define RWMPT_FAST_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(10) X(13)
 #define RWMPT_IEEE_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
 
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool SPLIT = false>
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
 cudaError_t launch_mcmc_one(const KernelArgs& a, const LaunchGeom& g, cudaStream_t st) {
-  auto kern = mcmc_kernel<Target, E, IEEE, WT, PF, EXACT, TEST, SPLIT>;
+  auto kern = mcmc_kernel<Target, E, IEEE, WT, PF, EXACT, TEST>;
   if (g.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
@@ -51,7 +51,7 @@ cudaError_t launch_mcmc_family(const KernelArgs& a, const LaunchGeom& g, bool ie
     }
   } else {
     cudaError_t e = Tuned<Target>::launch(a, g, st);
-    if (e != cudaErrorNotSupported || g.split) return e;
+    if (e != cudaErrorNotSupported) return e;
     switch (g.E) {
 #define X(e) case e: return launch_mcmc_one<Target, e, false, 0, -1, false, false>(a, g, st);
       RWMPT_FAST_E_LIST(X)
@@ -102,11 +102,8 @@ RWMPT_FAMILY_LIST(X)
 #undef X
 
 // RWMPT_DEFINE_TUNED(cls, LIST) with LIST(X) = X(E, W, PF) ... specialises Tuned<cls>
-#define RWMPT_SPLIT_CASE(cls, e, w, pf)                                                                    \
-  if (g.split && g.E == e && g.W == w && a.prop_family == pf && a.dim == e * w)                           \
-    return launch_mcmc_one<cls, e, false, w, pf, true, false, true>(a, g, st);
 #define RWMPT_TUNED_CASE(cls, e, w, pf)                                                        \
-  if (!g.split && g.E == e && g.W == w && a.prop_family == pf) {                              \
+  if (g.E == e && g.W == w && a.prop_family == pf) {                              \
     if (a.dim == e * w) return launch_mcmc_one<cls, e, false, w, pf, true, false>(a, g, st);  \
     return launch_mcmc_one<cls, e, false, w, pf, false, false>(a, g, st);                     \
   }
