@@ -89,8 +89,8 @@ def load():
     with _lock:
         if _lib is None:
             if not os.path.exists(LIB_PATH):
-                from . import build as _build
-                _build.build()
+                import importlib
+                importlib.import_module(__package__ + ".build").build()
             lib = C.CDLL(LIB_PATH)
             _declare(lib)
             if lib.rwmpt_sizeof_run_args() != C.sizeof(RunArgs):

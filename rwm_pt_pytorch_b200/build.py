@@ -80,6 +80,7 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), tag: 
 
 
 if __name__ == "__main__":
+    NVCC_FLAGS.extend(a[7:] for a in sys.argv if a.startswith("--nvcc="))   # extra raw nvcc flags for A/B builds
     defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
     tags = [a[6:] for a in sys.argv if a.startswith("--tag=")]
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, tag=tags[0] if tags else "")

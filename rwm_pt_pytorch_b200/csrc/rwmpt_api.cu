@@ -201,6 +201,7 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
     a.rk[2 * q + 1] = a.key1 + (unsigned)q * 0xBB67AE85u;
   }
   a.chain_id_base = r->chain_id_base;
+  a.target_plain = r->target.n_params < RWMPT_PARAM_HEADER + d ? 1 : 0;
   a.samples = r->samples; a.sample_logp = r->sample_logp;
   a.store_start = r->store_start; a.thin = r->thin < 1 ? 1 : r->thin; a.sample_stride = r->sample_stride; a.sample_rows = r->sample_rows;
   a.accept_count = r->accept_count; a.sq_jump_sum = r->sq_jump_sum;

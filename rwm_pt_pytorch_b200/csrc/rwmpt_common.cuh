@@ -48,6 +48,7 @@ struct KernelArgs {
   unsigned char* decisions;
   unsigned char* swap_dec;
   long long n_ladders;
+  int target_plain;  // the target has no per-coordinate scaling block (RoughCarpet: n_params == header)
   int stage_rows;  // rows per chain staged in shared memory before a coalesced flush
   int stage_off;   // offset (floats) of the staging region in dynamic shared memory
   int stage_vw;    // floats per vector store of the flush (4, 2 or 1)

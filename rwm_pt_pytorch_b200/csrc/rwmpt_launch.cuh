@@ -107,6 +107,12 @@ RWMPT_FAMILY_LIST(X)
     if (a.dim == e * w) return launch_mcmc_one<cls, e, false, w, pf, true, false>(a, g, st);  \
     return launch_mcmc_one<cls, e, false, w, pf, false, false>(a, g, st);                     \
   }
+// tuned case that swaps in a leaner functor (e.g. RoughCarpetPlain) when the target carries no scaling block
+#define RWMPT_TUNED_PLAIN_CASE(cls, plain, e, w, pf)                                               \
+  if (a.target_plain && g.E == e && g.W == w && a.prop_family == pf) {                             \
+    if (a.dim == e * w) return launch_mcmc_one<plain, e, false, w, pf, true, false>(a, g, st);    \
+    return launch_mcmc_one<plain, e, false, w, pf, false, false>(a, g, st);                       \
+  }
 #define RWMPT_DEFINE_TUNED(cls, LIST)                                                              \
   namespace rwmpt {                                                                                \
   template <>                                                                                      \

@@ -14,8 +14,10 @@ namespace rwmpt {
 #define RWMPT_NEG_INF (__int_as_float(0xff800000))
 
 // ---- RoughCarpetDistributionTorch.log_density, multimodal_torch.py:470-510 ---------------------
-template <int E, bool IEEE>
-struct RoughCarpet {
+// SCALED = false: instantiated for the tuned kernels when the target carries no per-coordinate scaling factors (the
+// common case), so the fast path does not multiply by 1.
+template <int E, bool IEEE, bool SCALED>
+struct RoughCarpetT {
   using M = Mth<IEEE>;
   float m0, m1, m2, lw0, lw1, lw2, lsp, J;
   float b0, b1, b2, c0, c1, c2;  // fast path: b_k = log2(e) m_k, c_k = log2(e) (lw_k - lsp - m_k^2 / 2)
@@ -61,18 +63,21 @@ struct RoughCarpet {
       // work in base 2.  t_k = h xs^2 + b_k xs + c_k (h = -log2(e)/2, b_k = log2(e) m_k, c_k = h m_k^2 + a_k): the
       // quadratic term is common to the three modes, so logsumexp_k t_k = h xs^2 + logsumexp_k (b_k xs + c_k);
       // and sum_i log2(S_i) = log2(prod_i S_i): one lg2 per lane instead of one per coordinate.
-      // The largest of the three terms contributes exactly 2^0 = 1, so only two ex2 are evaluated per coordinate:
-      // S = 1 + 2^(mid - max) + 2^(min - max), mid = (l0 + l1 + l2) - max - min.  Sums / products are combined as
-      // trees (two accumulators) to shorten the dependent chain.
+      // Sums / products are combined as trees (two accumulators) to shorten the dependent chain.  (RWMPT_RC_EXP2: the
+      // largest term is exactly 2^0, so two ex2 + min/mid arithmetic instead of three ex2 -- fewer SFU ops, more issue slots.)
       float hs[2] = {0.0f, 0.0f}, ps[2] = {1.0f, 1.0f}, qs[2] = {0.0f, 0.0f};
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        const float xs = x[e] * s[e];
+        const float xs = SCALED ? x[e] * s[e] : x[e];
         const float l0 = fmaf(b0, xs, c0), l1 = fmaf(b1, xs, c1), l2 = fmaf(b2, xs, c2);
         const float mx = fmaxf(fmaxf(l0, l1), l2);
+#ifdef RWMPT_RC_EXP2
         const float lo = fminf(fminf(l0, l1), l2);
         const float mid = ((l0 + l1) + l2) - (mx + lo);
         const float ss = (1.0f + ex2_approx(mid - mx)) + ex2_approx(lo - mx);
+#else
+        const float ss = (ex2_approx(l0 - mx) + ex2_approx(l1 - mx)) + ex2_approx(l2 - mx);
+#endif
         qs[e & 1] = fmaf(xs, xs, qs[e & 1]);  // padding coordinates hold xs = 0
         hs[e & 1] += c.ok(e) ? mx : 0.0f;
         ps[e & 1] *= c.ok(e) ? ss : 1.0f;
@@ -84,6 +89,11 @@ struct RoughCarpet {
     }
   }
 };
+
+template <int E, bool IEEE>
+using RoughCarpet = RoughCarpetT<E, IEEE, true>;
+template <int E, bool IEEE>
+using RoughCarpetPlain = RoughCarpetT<E, IEEE, false>;
 
 // ---- ThreeMixtureDistributionTorch.log_density, multimodal_torch.py:173-242 --------------------
 template <int E, bool IEEE>
