@@ -3,7 +3,7 @@
 
 Same constructor arguments (same order), methods and attributes as the reference.  New optional keyword
 arguments are appended at the end only: `num_chains` (batch of independent chains in one launch), `seed`,
-`store`, `thin`, `math_mode`, `initial_states`, `chain_id_base`, `lanes_per_chain`.
+`store`, `thin`, `math_mode`, `initial_states`, `chain_id_base`, `lanes_per_chain`, `proposal_scales`.
 
 Differences that are deliberate: the Python per-step loop, the pre-generated (T, d) random
 tensors and the per-step `.item()` sync are gone -- one kernel launch runs all burn_in + num_samples steps with
@@ -45,7 +45,8 @@ class RandomWalkMH_GPU_Optimized(MHAlgorithm):
                  math_mode: str = "fast",
                  initial_states=None,
                  chain_id_base: int = 0,
-                 lanes_per_chain: int = 0):
+                 lanes_per_chain: int = 0,
+                 proposal_scales=None):
         if not isinstance(target_dist, TorchTargetDistribution):
             raise TypeError("RandomWalkMH_GPU_Optimized needs a TorchTargetDistribution from "
                             "rwm_pt_pytorch_b200.target_distributions (the legacy NumPy-density path of the "
@@ -91,6 +92,11 @@ class RandomWalkMH_GPU_Optimized(MHAlgorithm):
             scales = np.sqrt((vars_ / betas).astype(np.float32)).astype(np.float32)     # normal.py:27-31
         else:
             scales = np.asarray([self.proposal_dist.chain_scale(float(b)) for b in betas], dtype=np.float32)
+        if proposal_scales is not None:
+            # explicit per-chain kernel scale (std / Laplace multiplier / ball radius): batches a whole scale sweep
+            scales = np.broadcast_to(np.asarray(proposal_scales, dtype=np.float32), (self.num_chains,)).copy()
+            if np.any(scales <= 0):
+                raise ValueError("proposal_scales must be positive")
         self._betas, self._scales = betas.astype(np.float32), scales
 
         self.num_acceptances = 0

@@ -615,3 +615,31 @@ def test_iterative_ladder_construction_runs_on_gpu_densities():
     assert p.get_name() == "PT_RWM_GPU_ULTRA_FUSED_ITERATIVE_LADDER"
     p.generate_samples(3000)
     assert 0.1 < p.swap_acceptance_rate < 0.6
+
+
+def test_batched_sweep_drivers_write_the_reference_schema(tmp_path):
+    """40-scale RWM sweep in one launch and a short PT sweep; JSON keys are the reference's (experiment_RWM_GPU.py:283-301,
+    experiment_pt_GPU.py:262-279); the ESJD-vs-acceptance curve has the familiar shape (optimum near 0.234)."""
+    import json
+    _cuda()
+    from rwm_pt_pytorch_b200.experiments import run_rwm_study, run_pt_study
+    out = run_rwm_study(20, "MultivariateNormal", num_iters=20000, var_max=3.5, seed=42, burn_in=1000,
+                        chains_per_value=64, out_dir=str(tmp_path))
+    ref_keys = {'target_distribution', 'proposal_distribution', 'dimension', 'num_iterations', 'seed', 'total_time', 'max_esjd',
+                'max_acceptance_rate', 'max_scale_param', 'expected_squared_jump_distances', 'acceptance_rates',
+                'scale_param_range', 'times'}
+    saved = json.load(open(out['filename']))
+    assert ref_keys <= set(saved) and len(saved['acceptance_rates']) == 40
+    acc = np.asarray(saved['acceptance_rates'])
+    assert acc[0] > 0.95 and np.all(np.diff(acc) < 0.02) and acc[-1] < 0.15          # monotone decreasing in the scale
+    assert 0.15 < saved['max_acceptance_rate'] < 0.35 and 2.0 < saved['max_scale_param'] < 2.9   # 0.234 rule, l* ~ 2.38
+    for prop in ("Laplace", "UniformRadius"):
+        o = run_rwm_study(10, "MultivariateNormal", num_iters=4000, var_max=3.0, seed=1, burn_in=200, proposal_name=prop,
+                          num_values=8, chains_per_value=32)
+        a = np.asarray(o['acceptance_rates'])
+        assert a[0] > 0.9 and a[-1] < a[0] and np.isfinite(o['expected_squared_jump_distances']).all()
+    pt = run_pt_study(5, "RoughCarpet", num_iters=4000, swap_accept_max=0.5, seed=3, burn_in=200, N_samples_swap_est=20000,
+                      iterative_tolerance=0.02, iterative_max_pn_steps=60, num_values=3, ladders_per_value=16, swap_every=5,
+                      out_dir=str(tmp_path))
+    assert {'max_actual_acceptance_rate', 'max_constr_acceptance_rate', 'swap_acceptance_rates_range'} <= set(pt)
+    assert len(pt['acceptance_rates']) == 3 and pt['acceptance_rates'][0] < pt['acceptance_rates'][-1]

@@ -189,3 +189,16 @@ def test_reference_aliases():
     finally:
         for n in ("algorithms", "interfaces", "proposal_distributions", "target_distributions"):
             sys.modules.pop(n, None)
+
+
+def test_experiment_target_factory_matches_reference_defaults():
+    from rwm_pt_pytorch_b200.experiments import get_target_distribution
+    t = get_target_distribution("RoughCarpet", 20, device="cpu")
+    assert t.get_name() == "RoughCarpetTorchCustom" and t.modes.tolist() == [-4.0, 0.0, 4.0]     # experiment_RWM_GPU.py:36
+    assert get_target_distribution("HybridRosenbrock", 0, device="cpu").dim == 11
+    assert get_target_distribution("Hypercube", 3, device="cpu").left_boundary.item() == -1.0
+    assert get_target_distribution("ThreeMixtureScaled", 4, device="cpu").get_name() == "ThreeMixtureTorchScaled"
+    with pytest.raises(ValueError):
+        get_target_distribution("Nope", 3, device="cpu")
+    with pytest.raises(NotImplementedError):
+        get_target_distribution("SuperFunnel", 3, device="cpu")
