@@ -89,6 +89,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=10)   # NVML polling stalls cudaMalloc / cudaFree of later phases: make sure it is gone
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -228,6 +232,8 @@ def e2e_run(wl, t, batch, dev_index, T, reps):
     a.lanes_per_chain = batch.lanes_per_chain
     h2d, d2h = C.c_uint64(), C.c_uint64()
     times = []
+    batch.run(T)                       # the set-up above left the GPU idle long enough to drop its clocks: ramp them up again
+    torch.cuda.synchronize()
     for i in range(reps + 1):
         state.copy_(state0); logp.copy_(logp0); acc.zero_(); sq.zero_(); sacc.zero_(); last.zero_()
         t0 = time.perf_counter()
@@ -235,6 +241,8 @@ def e2e_run(wl, t, batch, dev_index, T, reps):
         dt = time.perf_counter() - t0
         if i > 0:
             times.append(dt)
+        if os.environ.get("RWMPT_BENCH_DEBUG"):
+            print(f"e2e call {i}: {dt * 1e3:.2f} ms", file=sys.stderr)
     accept = float(acc.sum().item()) / max(nc * (T - wl["burn_in"]), 1)
     return float(np.mean(times)), int(h2d.value), int(d2h.value), accept
 

@@ -1,6 +1,6 @@
 // Instantiates the fused RWM / PT-RWM kernel and the batched log-density kernel for the ThreeMixture target,
 // plus the tuned (compile-time lanes-per-chain / proposal family) variants used by the BASELINE workloads.
 #include "rwmpt_launch.cuh"
-#define TUNED_LIST(cls) RWMPT_TUNED_CASE(cls, 13, 4, 1) RWMPT_TUNED_CASE(cls, 13, 4, 2) RWMPT_TUNED_CASE(cls, 8, 8, 1) RWMPT_TUNED_CASE(cls, 8, 8, 2) RWMPT_TUNED_CASE(cls, 4, 16, 1) RWMPT_TUNED_CASE(cls, 4, 16, 2)
+#define TUNED_LIST(cls) RWMPT_TUNED_CASE(cls, 13, 4, 1) RWMPT_TUNED_CASE(cls, 13, 4, 2)
 RWMPT_DEFINE_TUNED(rwmpt::ThreeMixture, TUNED_LIST)
 RWMPT_DEFINE_FAMILY(three_mixture, ThreeMixture)

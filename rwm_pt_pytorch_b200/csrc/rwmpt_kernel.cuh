@@ -477,17 +477,13 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
   } else if (a.n_steps > 0) {
     // Software pipeline: the increments of the NEXT pair of steps are drawn while the current pair's density /
     // reduction / accept chain is in flight (they do not depend on the state).  Steps with an "event" (sweep due,
-    // sample to retain, accumulator flush, burn-in boundary, end of run) go through do_step; all other pairs run
-    // plain_step twice with no branch at all.
+    // sample to retain, accumulator flush, burn-in boundary, start / end of run inside a pair) go through do_step; all
+    // other pairs run plain_step twice with no branch at all.
     float iA[E], iB[E], uA, uB;
     unsigned long long pair = (unsigned long long)(s_first - 1) >> 1;
     draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, pair, chain_gid, scale, dscale);
     long long t = 0;
-    if ((s_first - 1) & 1) {  // the run starts on the second step of a pair
-      do_step(iB, uB, t);
-      ++t; ++pair;
-      draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, pair, chain_gid, scale, dscale);
-    }
+    int h0 = (int)((s_first - 1) & 1);  // 1: the run starts on the second step of a pair
     while (t < a.n_steps) {
       // first local step >= t that needs the general path
       long long ev = t | 63;                                   // accumulator flush
@@ -496,43 +492,15 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       if (K > 1 && t + swap_cd < ev) ev = t + swap_cd;         // sweep due after that step
       if (a.samples != nullptr && !store_each && t + store_cd < ev) ev = t + store_cd;
       const bool post = t >= burn_t;
-      const long long n_fast = (ev - t) >> 1;                  // whole pairs strictly before the event
+      const long long n_fast = h0 ? 0 : (ev - t) >> 1;         // whole pairs strictly before the event
       auto fast_pairs = [&](auto store_tag) {
-      for (long long q = 0; q < n_fast; ++q) {
+        for (long long q = 0; q < n_fast; ++q) {
           float nA[E], nB[E], vA, vB;
-  #ifndef RWMPT_ORDER
-  #define RWMPT_ORDER 0
-  #endif
-  #if RWMPT_ORDER == 0
-          draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
-          plain_step(iA, uA, post, store_tag);
-          plain_step(iB, uB, post, store_tag);
-  #elif RWMPT_ORDER == 1
           plain_step(iA, uA, post, store_tag);
           draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
           plain_step(iB, uB, post, store_tag);
-  #elif RWMPT_ORDER == 2
-          PairWords<E, PF> pw;
-          pw.init(c, pair + 1, chain_gid);
-          pw.template rounds<0, 10>(a);
-          plain_step(iA, uA, post, store_tag);
-          pair_transform<E, IEEE, PF>(a, c, pw.w, nA, nB, vA, vB, scale, dscale);
-          plain_step(iB, uB, post, store_tag);
-  #elif RWMPT_ORDER == 3
-          PairWords<E, PF> pw;
-          pw.init(c, pair + 1, chain_gid);
-          pw.template rounds<0, 5>(a);
-          plain_step(iA, uA, post, store_tag);
-          pw.template rounds<5, 10>(a);
-          plain_step(iB, uB, post, store_tag);
-          pair_transform<E, IEEE, PF>(a, c, pw.w, nA, nB, vA, vB, scale, dscale);
-  #elif RWMPT_ORDER == 4
-          plain_step(iA, uA, post, store_tag);
-          plain_step(iB, uB, post, store_tag);
-          draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
-  #endif
           ++pair;
-  #pragma unroll
+#pragma unroll
           for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
           uA = vA; uB = vB;
         }
@@ -543,16 +511,20 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       t += 2 * n_fast;
       if (K > 1) swap_cd -= 2 * n_fast;
       if (a.samples != nullptr) store_cd -= 2 * n_fast;
-      // the pair that holds the event, through the general path
+      // the pair that holds the event, through the general path (one copy of do_step: the two halves share the code)
       {
         float nA[E], nB[E], vA, vB;
         draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
-        do_step(iA, uA, t);
-        ++t;
-        if (t < a.n_steps) {
-          do_step(iB, uB, t);
+#pragma unroll 1
+        for (int h = h0; h < 2; ++h) {
+          if (t >= a.n_steps) break;
+          float inc[E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) inc[e] = h ? iB[e] : iA[e];
+          do_step(inc, h ? uB : uA, t);
           ++t;
         }
+        h0 = 0;
         ++pair;
 #pragma unroll
         for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }

@@ -7,7 +7,7 @@
 namespace rwmpt {
 
 // elements-per-lane (E) variants compiled for each math mode; the picker in rwmpt_api.cu uses the same lists
-#define RWMPT_FAST_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(10) X(13)
+#define RWMPT_FAST_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
 #define RWMPT_IEEE_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
 
 template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
