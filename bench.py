@@ -230,6 +230,7 @@ def e2e_run(wl, t, batch, dev_index, T, reps):
     a.accept_count, a.sq_jump_sum = acc.data_ptr(), sq.data_ptr()
     a.swap_accepts, a.swap_last_attempt = sacc.data_ptr(), last.data_ptr()
     a.lanes_per_chain = batch.lanes_per_chain
+    a.schedule = batch.schedule
     h2d, d2h = C.c_uint64(), C.c_uint64()
     times = []
     batch.run(T)                       # the set-up above left the GPU idle long enough to drop its clocks: ramp them up again

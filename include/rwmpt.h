@@ -65,6 +65,9 @@ enum { RWMPT_SWAP_REFERENCE = 0, RWMPT_SWAP_EXCHANGE = 1 };
 enum { RWMPT_MATH_FAST = 0, RWMPT_MATH_IEEE = 1 };
 /* Trajectory storage: nothing / temperature 0 of every ladder / every chain.                   */
 enum { RWMPT_STORE_NONE = 0, RWMPT_STORE_COLD = 1, RWMPT_STORE_ALL = 2 };
+/* AUTO: balanced when a plain launch would load the SMs' warp schedulers unevenly (few warps per scheduler);
+   PLAIN: one CTA per unit for the whole run; BALANCED: SM-sized grid, time-sliced units handed out by ticket. */
+enum { RWMPT_SCHEDULE_AUTO = 0, RWMPT_SCHEDULE_PLAIN = 1, RWMPT_SCHEDULE_BALANCED = 2 };
 
 typedef struct {
   int32_t family;      /* RWMPT_T_*                                  */
@@ -130,7 +133,8 @@ typedef struct {
   unsigned char* decisions;        /* [n_steps, n_chains] out, nullable                                  */
   unsigned char* swap_decisions;   /* [n_rounds, n_ladders, n_temps-1] out, nullable                     */
   int32_t lanes_per_chain;         /* 0 = auto; else power of two <= 32: threads cooperating on a chain  */
-  int32_t reserved;
+  int32_t schedule;                /* RWMPT_SCHEDULE_*: how units of work (CTAs of whole ladders / chain groups)
+                                      are placed on the SMs; results never depend on it                    */
 } rwmpt_run_args_t;
 
 int rwmpt_version(void);

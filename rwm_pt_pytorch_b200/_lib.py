@@ -48,7 +48,7 @@ class RunArgs(C.Structure):
         ("swap_accepts", C.c_void_p), ("swap_last_attempt", C.c_void_p),
         ("inj_increments", C.c_void_p), ("inj_uniforms", C.c_void_p), ("inj_swap_uniforms", C.c_void_p),
         ("decisions", C.c_void_p), ("swap_decisions", C.c_void_p),
-        ("lanes_per_chain", C.c_int32), ("reserved", C.c_int32),
+        ("lanes_per_chain", C.c_int32), ("schedule", C.c_int32),
     ]
 
 

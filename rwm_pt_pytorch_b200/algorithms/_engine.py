@@ -5,6 +5,8 @@ Nothing here computes on the host: states, log-densities, accumulators and retai
 torch tensors (torch = device memory + streams only) and every sampling step runs in librwmpt.so."""
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Optional
 
@@ -36,6 +38,9 @@ class LadderBatch:
         self.rng_generator = rng_generator
         self.chain_id_base = int(chain_id_base)
         self.lanes_per_chain = int(lanes_per_chain)
+        # how units of work are placed on the SMs (include/rwmpt.h RWMPT_SCHEDULE_*: 0 auto, 1 plain, 2 balanced);
+        # results never depend on it.  RWMPT_SCHEDULE overrides the default for A/B measurements.
+        self.schedule = int(os.environ.get("RWMPT_SCHEDULE", "0"))
         dev = self.device
         f32 = dict(device=dev, dtype=torch.float32)
         self.beta = torch.as_tensor(np.broadcast_to(np.asarray(betas, dtype=np.float32), (self.L, self.K)).copy()).to(dev).reshape(-1).contiguous()
@@ -140,6 +145,7 @@ class LadderBatch:
         a.swap_accepts = self.swap_accepts.data_ptr()
         a.swap_last_attempt = self.swap_last_attempt.data_ptr()
         a.lanes_per_chain = self.lanes_per_chain
+        a.schedule = self.schedule
         keep = []
         if inj_increments is not None:
             inc = torch.as_tensor(inj_increments).to(device=dev, dtype=torch.float32).reshape(n_steps, self.n_chains, self.dim).contiguous()

@@ -40,7 +40,7 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, defines: tuple = (), tag: str = "") -> str:
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), tag: str = "", only: tuple = ()) -> str:
     """Compile every .cu under csrc/ for sm_100a and link librwmpt.so; returns the library path.
     `defines` / `tag` build an experimental variant (librwmpt_<tag>.so) with extra -D flags."""
     global OBJ, LIB
@@ -52,11 +52,17 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), tag: 
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     nvcc = _nvcc()
     jobs = []
+    objs = []
+    main_obj = os.path.join(PKG, "build")
     for src in sources:
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        stem = os.path.basename(src)[:-3]
+        if tag and only and not any(o in stem for o in only):
+            objs.append(os.path.join(main_obj, stem + ".o"))  # variant build: untouched families come from the main build
+            continue
+        obj = os.path.join(OBJ, stem + ".o")
+        objs.append(obj)
         if force or _stale(obj, [src] + headers):
             jobs.append((src, obj))
-    objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in sources]
 
     def compile_one(job):
         src, obj = job
@@ -83,5 +89,6 @@ if __name__ == "__main__":
     NVCC_FLAGS.extend(a[7:] for a in sys.argv if a.startswith("--nvcc="))   # extra raw nvcc flags for A/B builds
     defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
     tags = [a[6:] for a in sys.argv if a.startswith("--tag=")]
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, tag=tags[0] if tags else "")
+    only = tuple(x for a in sys.argv if a.startswith("--only=") for x in a[7:].split(","))  # with --tag: rebuild these TUs only
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, tag=tags[0] if tags else "", only=only)
     print(path)

@@ -183,6 +183,16 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   rc = pick_geometry(d, r->n_temps, r->n_ladders, ieee, r->lanes_per_chain, &g);
   if (rc) return rc;
   if (g.grid > 2147483647LL) return fail(RWMPT_ENOTSUP, "too many CTAs (%lld)", g.grid);
+  if (r->schedule < RWMPT_SCHEDULE_AUTO || r->schedule > RWMPT_SCHEDULE_BALANCED)
+    return fail(RWMPT_EINVAL, "unknown schedule %d", r->schedule);
+  {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+    g.sms = sms;
+    g.schedule = r->schedule;
+    // injected randomness / decision outputs (test mode) always run the plain schedule
+    if (r->inj_increments || r->decisions || r->swap_decisions) g.schedule = RWMPT_SCHEDULE_PLAIN;
+  }
 
   KernelArgs a;
   memset(&a, 0, sizeof(a));

@@ -52,6 +52,12 @@ struct KernelArgs {
   int stage_rows;  // rows per chain staged in shared memory before a coalesced flush
   int stage_off;   // offset (floats) of the staging region in dynamic shared memory
   int stage_vw;    // floats per vector store of the flush (4, 2 or 1)
+  // balanced (time-sliced, ticketed) launch -- see mcmc_kernel; n_slices <= 1: plain launch, CTA b runs unit b
+  int n_slices;
+  int n_units;            // CTAs of the plain launch (= units of work)
+  long long slice_steps;  // steps per slice (even)
+  unsigned* ticket;       // [1] zero-initialised
+  int* unit_done;         // [n_units] zero-initialised: slices published per unit
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -117,6 +123,38 @@ __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Blackwell packed fp32 (FFMA2 / FADD2 / FMUL2): two fp32 operations per issued instruction.  The fused kernel is
+// bound by instruction issue, not by the fp32 pipe, so the density loops pack adjacent coordinates.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 
 constexpr float kLog2e = 1.4426950408889634f;

@@ -22,7 +22,17 @@
 #include "rwmpt_common.cuh"
 #include "rwmpt_targets.cuh"
 
+#ifndef RWMPT_ORDER
+#define RWMPT_ORDER 0  // source order of the three streams inside the fast loop (ptxas keeps it as a tie-break)
+#endif
+
 namespace rwmpt {
+
+#ifdef RWMPT_NO_F32X2
+constexpr bool kUseF32x2 = false;
+#else
+constexpr bool kUseF32x2 = true;  // packed fp32 (FFMA2 / FADD2 / FMUL2) in the fast-math paths
+#endif
 
 // ---- Philox with the 10 round keys precomputed on the host (uniform operands from the argument block) -----
 __device__ __forceinline__ uint4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const KernelArgs& a) {
@@ -60,29 +70,84 @@ __host__ __device__ constexpr int pair_words(int E, int PF) {
 // scaling, and the chain's accept uniforms (taken from the leader lane).  Drawing two steps at once uses every
 // Philox word (E=5, Normal: 3 calls per 2 steps) and gives the scheduler three independent Philox chains.
 // PF >= 0: proposal family known at compile time; PF < 0: runtime switch on a.prop_family.
-// Philox words of one lane for one pair of steps, computed in stages so that the rounds can be spliced between
-// the phases of the Metropolis steps they overlap with (ptxas keeps source order among independent instructions).
+//
+// Counter layout of call k of lane `sub`:  c0 = (pair >> 32) << 16 | sub << 8 | k,  c1 = (uint32) pair,
+// (c2, c3) = global chain id; key = seed.  Only c1 -- an XOR input of the first round -- changes from pair to pair, so
+// everything that does not depend on it is evaluated once per run (PhiloxPairGen): round 1 costs one XOR shared by the
+// lane's calls, round 2 one multiply (shared) and one XOR, round 3 one multiply and two XORs; rounds 4..10 are plain.
+// The words are bit-identical to philox4x32_10 on that counter (PairWords / tests/test_gpu_parity.py resume tests).
+__host__ __device__ __forceinline__ void mulhilo32(uint32_t m, uint32_t x, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+  unsigned long long p;
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(x), "r"(m));
+  hi = (uint32_t)(p >> 32); lo = (uint32_t)p;
+#else
+  const uint64_t p = (uint64_t)m * x;
+  hi = (uint32_t)(p >> 32); lo = (uint32_t)p;
+#endif
+}
+
+__host__ __device__ __forceinline__ uint32_t pair_c0(unsigned long long pair, int sub, int k) {
+  return ((uint32_t)(pair >> 32) << 16) | ((uint32_t)sub << 8) | (uint32_t)k;
+}
+
 template <int E, int PF>
 struct PairWords {
   static constexpr int NW = pair_words(E, PF);
   static constexpr int NC = (NW + 3) / 4;
   uint32_t w[4 * NC];
-  template <class C>
-  __device__ __forceinline__ void init(const C& c, unsigned long long pair, unsigned long long chain_gid) {
-    const uint32_t c0 = (uint32_t)pair;
-    const uint32_t c1hi = ((uint32_t)(pair >> 32) << 16) | ((uint32_t)c.sub << 8);
+  // reference evaluation: ten plain rounds per call
+  __host__ __device__ __forceinline__ void full(const uint32_t* rk, int sub, unsigned long long pair, unsigned long long chain_gid) {
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-      w[4 * k + 0] = c0; w[4 * k + 1] = c1hi | (uint32_t)k;
-      w[4 * k + 2] = (uint32_t)chain_gid; w[4 * k + 3] = (uint32_t)(chain_gid >> 32);
+      uint32_t c0 = pair_c0(pair, sub, k), c1 = (uint32_t)pair, c2 = (uint32_t)chain_gid, c3 = (uint32_t)(chain_gid >> 32);
+#pragma unroll
+      for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, rk[2 * r], rk[2 * r + 1]);
+      w[4 * k] = c0; w[4 * k + 1] = c1; w[4 * k + 2] = c2; w[4 * k + 3] = c3;
     }
   }
-  template <int R0, int R1>
-  __device__ __forceinline__ void rounds(const KernelArgs& a) {
+};
+
+template <int NC>
+struct PhiloxPairGen {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t A1;                            // round 1: n0 = c1 ^ A1 (same for every call of the lane)
+  uint32_t B2[NC], C3[NC], D3[NC], E4[NC];  // per-call invariants of rounds 2..4
+  uint32_t hi32;                          // pair >> 32 the invariants were built for
+  __host__ __device__ __forceinline__ void init(const uint32_t* rk, int sub, unsigned long long pair, unsigned long long chain_gid) {
+    hi32 = (uint32_t)(pair >> 32);
+    const uint32_t c2 = (uint32_t)chain_gid, c3 = (uint32_t)(chain_gid >> 32);
+    uint32_t h1, l1;
+    mulhilo32(M1, c2, h1, l1);
+    A1 = h1 ^ rk[0];
 #pragma unroll
-    for (int r = R0; r < R1; ++r) {
+    for (int k = 0; k < NC; ++k) {
+      uint32_t h0, l0, h1p, l1p, h0pp, l0pp;
+      mulhilo32(M0, pair_c0(pair, sub, k), h0, l0);
+      const uint32_t N2 = h0 ^ c3 ^ rk[1];         // round 1 -> (c1 ^ A1, l1, N2, l0)
+      mulhilo32(M1, N2, h1p, l1p);
+      const uint32_t N0p = h1p ^ l1 ^ rk[2];       // round 2 -> (N0p, l1p, hi(M0 n0) ^ B2, lo(M0 n0))
+      B2[k] = l0 ^ rk[3];
+      mulhilo32(M0, N0p, h0pp, l0pp);              // round 3 -> (hi(M1 n2') ^ C3, lo(M1 n2'), lo(M0 n0) ^ D3, l0pp)
+      C3[k] = l1p ^ rk[4];
+      D3[k] = h0pp ^ rk[5];
+      E4[k] = l0pp ^ rk[7];                        // round 4: n2 = hi(M0 x0) ^ E4
+    }
+  }
+  __host__ __device__ __forceinline__ void gen(const uint32_t* rk, uint32_t pair_lo, uint32_t (&w)[4 * NC]) const {
+    uint32_t hA, lA;
+    mulhilo32(M0, pair_lo ^ A1, hA, lA);           // rounds 1 and 2, shared by the lane's calls
 #pragma unroll
-      for (int k = 0; k < NC; ++k) philox_round(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3], a.rk[2 * r], a.rk[2 * r + 1]);
+    for (int k = 0; k < NC; ++k) {
+      uint32_t h1, l1v, h0, l0n, h1b, l1n;
+      mulhilo32(M1, hA ^ B2[k], h1, l1v);          // round 3
+      const uint32_t x0 = h1 ^ C3[k], x2 = lA ^ D3[k];
+      mulhilo32(M0, x0, h0, l0n);                  // round 4
+      mulhilo32(M1, x2, h1b, l1n);
+      uint32_t c0 = h1b ^ l1v ^ rk[6], c1 = l1n, c2 = h0 ^ E4[k], c3 = l0n;
+#pragma unroll
+      for (int r = 4; r < 10; ++r) philox_round(c0, c1, c2, c3, rk[2 * r], rk[2 * r + 1]);
+      w[4 * k] = c0; w[4 * k + 1] = c1; w[4 * k + 2] = c2; w[4 * k + 3] = c3;
     }
   }
 };
@@ -112,6 +177,34 @@ __device__ __forceinline__ void pair_transform(const KernelArgs& a, const C& c, 
     }
     return;
   }
+#ifndef RWMPT_NO_F32X2
+  if constexpr (!IEEE && PF == RWMPT_P_NORMAL && E >= 2) {
+    // Packed-fp32 Box-Muller: two (radius, angle) pairs per FFMA2 / FMUL2.  The 2E normals of the lane are iid, so they
+    // are dealt to the coordinates of the two steps in the order that leaves (e, e+1) in one register pair.
+    constexpr int H = E / 2;
+    const float rs2s = -2.0f * kLn2 * scale * scale;
+    const f32x2_t RS2 = pack2(rs2s, rs2s);
+    const f32x2_t KU = pack2(2.3283064365386963e-10f, 2.3283064365386963e-10f);
+    const f32x2_t KU0 = pack2(1.1641532182693481e-10f, 1.1641532182693481e-10f);
+    const f32x2_t KT = pack2(1.4629180792671596e-9f, 1.4629180792671596e-9f);
+#pragma unroll
+    for (int g = 0; g < H; ++g) {
+      float ua, ub, ta, tb, qa, qb;
+      unpack2(fma2(pack2((float)w[4 * g], (float)w[4 * g + 2]), KU, KU0), ua, ub);
+      unpack2(mul2(pack2((float)w[4 * g + 1], (float)w[4 * g + 3]), KT), ta, tb);
+      unpack2(mul2(RS2, pack2(lg2_approx(ua), lg2_approx(ub))), qa, qb);
+      const f32x2_t r = pack2(sqrt_approx(qa), sqrt_approx(qb));
+      float z0, z1, z2, z3;
+      unpack2(mul2(r, pack2(__cosf(ta), __cosf(tb))), z0, z1);
+      unpack2(mul2(r, pack2(__sinf(ta), __sinf(tb))), z2, z3);
+      // pair slots 2g and 2g+1: the first H slots belong to step A, the rest to step B
+      if (2 * g < H) { incA[4 * g] = z0; incA[4 * g + 1] = z1; } else { incB[4 * g - 2 * H] = z0; incB[4 * g - 2 * H + 1] = z1; }
+      if (2 * g + 1 < H) { incA[4 * g + 2] = z2; incA[4 * g + 3] = z3; } else { incB[4 * g + 2 - 2 * H] = z2; incB[4 * g + 3 - 2 * H] = z3; }
+    }
+    if constexpr (E & 1) box_muller<false>(w[4 * H], w[4 * H + 1], incA[E - 1], incB[E - 1], rs2s);
+    return;
+  }
+#endif
   float z[2 * E];
   const bool fold = !IEEE && pf == RWMPT_P_NORMAL;  // normal.py:47-55: randn * std
   const float rs2 = fold ? -2.0f * kLn2 * scale * scale : -2.0f * kLn2;
@@ -152,9 +245,18 @@ __device__ __forceinline__ void draw_pair(const KernelArgs& a, const C& c, float
                                           float& uB, unsigned long long pair, unsigned long long chain_gid, float scale,
                                           const float (&dscale)[E]) {
   PairWords<E, PF> pw;
-  pw.init(c, pair, chain_gid);
-  pw.template rounds<0, 10>(a);
+  pw.full(a.rk, c.sub, pair, chain_gid);
   pair_transform<E, IEEE, PF>(a, c, pw.w, incA, incB, uA, uB, scale, dscale);
+}
+
+// same words through the run-invariant partial evaluation (the caller keeps gen.hi32 == pair >> 32)
+template <int E, bool IEEE, int PF, class C>
+__device__ __forceinline__ void draw_pair_fast(const KernelArgs& a, const C& c, const PhiloxPairGen<PairWords<E, PF>::NC>& gen,
+                                               float (&incA)[E], float (&incB)[E], float& uA, float& uB, uint32_t pair_lo,
+                                               float scale, const float (&dscale)[E]) {
+  uint32_t w[4 * PairWords<E, PF>::NC];
+  gen.gen(a.rk, pair_lo, w);
+  pair_transform<E, IEEE, PF>(a, c, w, incA, incB, uA, uB, scale, dscale);
 }
 
 // One uniform per (ladder, sweep, pair) on a separate Philox key.
@@ -184,11 +286,12 @@ __device__ __forceinline__ bool swap_accept(float bj, float bk, float lj, float 
   return u < p;  // NaN -> false
 }
 
-// Template parameters: Target functor; E coordinates per lane; IEEE parity arithmetic; WT lanes per chain (0 = runtime);
-// PF proposal family (-1 = runtime); EXACT: E*W == dim (no padding masks); TEST: injected randomness / decision
-// outputs available.
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
-__global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a) {
+// One unit of work: the chains of CTA index `cta` (whole ladders) advanced by `n_steps` steps from global step
+// `step_offset`.  SLICED: the unit is one time slice of a balanced launch -- another CTA (possibly on another SM) ran
+// the previous slice, so state is read past L1 and the accumulators are updated with atomics.
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool SLICED>
+__device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long cta, const long long step_offset,
+                                          const long long n_steps, const long long rounds_before) {
   using M = Mth<IEEE>;
   extern __shared__ float smem[];
 
@@ -205,7 +308,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
   c.leader = c.lane & ~(W - 1);
 
   const bool in_cta = cl < a.chains_per_cta;
-  const long long chain_raw = (long long)blockIdx.x * a.chains_per_cta + cl;
+  const long long chain_raw = cta * a.chains_per_cta + cl;
   const bool valid = in_cta && chain_raw < a.n_chains;
   const long long chain = valid ? chain_raw : 0;  // dummy threads shadow chain 0 but never write
   const int temp = cl % K;  // chains_per_cta is a multiple of K, so this is also chain % K
@@ -221,14 +324,14 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int i = c.base + e;
-    x[e] = (i < d) ? a.state[chain * d + i] : 0.0f;
+    x[e] = (i < d) ? (SLICED ? __ldcg(a.state + chain * d + i) : a.state[chain * d + i]) : 0.0f;
     dscale[e] = (i < d && a.prop_dim_scale) ? a.prop_dim_scale[i] : 1.0f;
   }
-  float lp = a.logp[chain];
+  float lp = SLICED ? __ldcg(a.logp + chain) : a.logp[chain];
   const float beta = a.beta[chain];
   const float scale = a.prop_scale ? a.prop_scale[chain] : 1.0f;
 
-  const long long s_first = a.step_offset + 1;
+  const long long s_first = step_offset + 1;
   // shared memory carve-up for the swap sweep
   float* s_lp = smem;                                  // [chains_per_cta]
   int* s_src = (int*)(smem + a.chains_per_cta);        // [chains_per_cta]
@@ -239,6 +342,10 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     if (in_cta && c.sub == 0) s_beta[cl] = beta;
     cta_sync();
   }
+  // A ladder whose K*W lanes sit inside one warp (BASELINE config 3: 8 temperatures x 4 lanes = the whole warp) sweeps
+  // with warp shuffles: no shared memory, no barrier, no branch.
+  const bool warp_ladder = K > 1 && K * W <= 32 && 32 % (K * W) == 0;
+  const float beta_next = warp_ladder ? __shfl_down_sync(kFull, beta, W) : 0.0f;
 
   // countdowns (no per-step modulo)
   long long swap_cd = -1;
@@ -302,13 +409,96 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     ++nbuf;
     if (nbuf == S) stage_flush();
   };
-  const long long burn_t = a.burn_in > a.step_offset ? a.burn_in - a.step_offset : 0;  // local steps t >= burn_t count
+  const long long burn_t = a.burn_in > step_offset ? a.burn_in - step_offset : 0;  // local steps t >= burn_t count
 
   unsigned long long n_acc = 0, n_swap_acc = 0, last_attempt = 0;
   unsigned n_acc32 = 0;
   long long round_local = 0;
   float jump_f = 0.0f;
   double jump_d = 0.0;
+
+  // ---- adjacent-temperature sweep of the CTA's ladders (pt_rwm_gpu_optimized.py:594-633); returns whether this
+  // thread's chain received a new state ------------------------------------------------------------------------
+  auto sweep = [&]() -> bool {
+    bool changed = false;
+    if (warp_ladder && a.swap_mode == RWMPT_SWAP_REFERENCE) {
+      // reference semantics (pt_rwm_gpu_optimized.py:594-633 with the copy k -> j of :50-59): pair j only rewrites
+      // slot j, from the PRE-sweep occupant of slot j+1 -- every pair decides at once on the pre-sweep values.
+      const unsigned long long round_g = (unsigned long long)(rounds_before + round_local);  // 0-based
+      const long long su_base = (round_local * a.n_ladders + ladder) * (K - 1);
+      const bool has_next = valid && temp < K - 1;
+      float us;
+      if (TEST && a.inj_su != nullptr) us = has_next ? a.inj_su[su_base + temp] : 2.0f;
+      else us = swap_uniform(a.key0, a.key1, ladder_gid, round_g, temp);
+      const float lp_n = __shfl_down_sync(kFull, lp, W);
+      float xn[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) xn[e] = __shfl_down_sync(kFull, x[e], W);
+      const bool ok = has_next && swap_accept<IEEE>(beta, beta_next, lp, lp_n, us);
+#pragma unroll
+      for (int e = 0; e < E; ++e) x[e] = ok ? xn[e] : x[e];
+      lp = ok ? lp_n : lp;
+      if (TEST && lead && a.swap_dec && has_next) a.swap_dec[su_base + temp] = ok ? 1 : 0;
+      n_swap_acc += ok ? 1ull : 0ull;
+      last_attempt = ok ? round_g * (unsigned long long)(K - 1) + temp + 1 : last_attempt;
+      round_local++;
+      return ok;
+    }
+    if (in_cta) {
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (c.base + e < d) s_x[cl * d + c.base + e] = x[e];
+      if (c.sub == 0) { s_lp[cl] = lp; s_src[cl] = cl; s_ok[cl] = 0; }
+    }
+    cta_sync();
+    const unsigned long long round_g = (unsigned long long)(rounds_before + round_local);  // 0-based
+    const long long su_base = (round_local * a.n_ladders + ladder) * (K - 1);
+    const bool inj_su = TEST && a.inj_su != nullptr;
+    if (a.swap_mode == RWMPT_SWAP_REFERENCE) {
+      // decisions of all pairs are independent here: pair j only ever rewrites slot j
+      bool ok = false;
+      if (valid && temp < K - 1) {
+        const float us = inj_su ? a.inj_su[su_base + temp] : swap_uniform(a.key0, a.key1, ladder_gid, round_g, temp);
+        ok = swap_accept<IEEE>(beta, s_beta[cl + 1], s_lp[cl], s_lp[cl + 1], us);
+        if (ok) {
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            if (c.base + e < d) x[e] = s_x[(cl + 1) * d + c.base + e];
+          lp = s_lp[cl + 1];
+          changed = true;
+        }
+        if (TEST && lead && a.swap_dec) a.swap_dec[su_base + temp] = ok ? 1 : 0;
+      }
+      if (ok) { n_swap_acc++; last_attempt = round_g * (unsigned long long)(K - 1) + temp + 1; }
+    } else {
+      // textbook exchange: sequential sweep by the ladder's first thread, then everyone gathers
+      if (valid && temp == 0 && c.sub == 0) {
+        for (int j = 0; j < K - 1; ++j) {
+          const int sa = s_src[cl + j], sb = s_src[cl + j + 1];
+          const float us = inj_su ? a.inj_su[su_base + j] : swap_uniform(a.key0, a.key1, ladder_gid, round_g, j);
+          const bool ok = swap_accept<IEEE>(s_beta[cl + j], s_beta[cl + j + 1], s_lp[sa], s_lp[sb], us);
+          if (ok) { s_src[cl + j] = sb; s_src[cl + j + 1] = sa; }
+          s_ok[cl + j] = ok ? 1 : 0;
+          if (TEST && a.swap_dec) a.swap_dec[su_base + j] = ok ? 1 : 0;
+        }
+      }
+      cta_sync();
+      if (valid) {
+        const int src = s_src[cl];
+        if (src != cl) {
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            if (c.base + e < d) x[e] = s_x[src * d + c.base + e];
+          lp = s_lp[src];
+          changed = true;
+        }
+        if (temp < K - 1 && s_ok[cl]) { n_swap_acc++; last_attempt = round_g * (unsigned long long)(K - 1) + temp + 1; }
+      }
+    }
+    round_local++;
+    cta_sync();  // s_x / s_lp are rewritten at the next sweep
+    return changed;
+  };
 
   // ---- one Metropolis step (+ sweep, accumulators, retained sample) with the given increments -----------------
   auto do_step = [&](const float (&inc)[E], const float u, const long long t) {
@@ -338,57 +528,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       if (swap_cd == 0) {
         swap_cd = a.swap_every;
         swapped_now = true;
-        if (in_cta) {
-#pragma unroll
-          for (int e = 0; e < E; ++e)
-            if (c.base + e < d) s_x[cl * d + c.base + e] = x[e];
-          if (c.sub == 0) { s_lp[cl] = lp; s_src[cl] = cl; s_ok[cl] = 0; }
-        }
-        cta_sync();
-        const unsigned long long round_g = (unsigned long long)(a.rounds_before + round_local);  // 0-based
-        const long long su_base = (round_local * a.n_ladders + ladder) * (K - 1);
-        const bool inj_su = TEST && a.inj_su != nullptr;
-        if (a.swap_mode == RWMPT_SWAP_REFERENCE) {
-          // decisions of all pairs are independent here: pair j only ever rewrites slot j
-          bool ok = false;
-          if (valid && temp < K - 1) {
-            const float us = inj_su ? a.inj_su[su_base + temp] : swap_uniform(a.key0, a.key1, ladder_gid, round_g, temp);
-            ok = swap_accept<IEEE>(beta, s_beta[cl + 1], s_lp[cl], s_lp[cl + 1], us);
-            if (ok) {
-#pragma unroll
-              for (int e = 0; e < E; ++e)
-                if (c.base + e < d) x[e] = s_x[(cl + 1) * d + c.base + e];
-              lp = s_lp[cl + 1];
-            }
-            if (TEST && lead && a.swap_dec) a.swap_dec[su_base + temp] = ok ? 1 : 0;
-          }
-          if (ok) { n_swap_acc++; last_attempt = round_g * (unsigned long long)(K - 1) + temp + 1; }
-        } else {
-          // textbook exchange: sequential sweep by the ladder's first thread, then everyone gathers
-          if (valid && temp == 0 && c.sub == 0) {
-            for (int j = 0; j < K - 1; ++j) {
-              const int sa = s_src[cl + j], sb = s_src[cl + j + 1];
-              const float us = inj_su ? a.inj_su[su_base + j] : swap_uniform(a.key0, a.key1, ladder_gid, round_g, j);
-              const bool ok = swap_accept<IEEE>(s_beta[cl + j], s_beta[cl + j + 1], s_lp[sa], s_lp[sb], us);
-              if (ok) { s_src[cl + j] = sb; s_src[cl + j + 1] = sa; }
-              s_ok[cl + j] = ok ? 1 : 0;
-              if (TEST && a.swap_dec) a.swap_dec[su_base + j] = ok ? 1 : 0;
-            }
-          }
-          cta_sync();
-          if (valid) {
-            const int src = s_src[cl];
-            if (src != cl) {
-#pragma unroll
-              for (int e = 0; e < E; ++e)
-                if (c.base + e < d) x[e] = s_x[src * d + c.base + e];
-              lp = s_lp[src];
-            }
-            if (temp < K - 1 && s_ok[cl]) { n_swap_acc++; last_attempt = round_g * (unsigned long long)(K - 1) + temp + 1; }
-          }
-        }
-        round_local++;
-        cta_sync();  // s_x / s_lp are rewritten at the next sweep
+        sweep();
       }
       swap_cd--;
     }
@@ -409,10 +549,9 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       for (int e = 0; e < E; ++e) j2 = c.ok(e) ? fmaf(inc[e], inc[e], j2) : j2;
       jump_f += (post && acc) ? j2 : 0.0f;
     }
-    if ((t & 63) == 63) {
-      jump_d += (double)jump_f; jump_f = 0.0f;
-      n_acc += n_acc32; n_acc32 = 0;
-    }
+    // the general path is rare (run edges, burn-in boundary, thinned stores): move the partial sums every time
+    jump_d += (double)jump_f; jump_f = 0.0f;
+    n_acc += n_acc32; n_acc32 = 0;
 
     // 8. retained samples: layout (chain, row, dim)
     if (a.samples != nullptr) {
@@ -429,42 +568,66 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     }
   };
 
-  // ---- plain step: no sweep, no retained sample, no flush -- a single basic block, so that ptxas can interleave it
-  // with the Philox / Box-Muller stream of the next pair of steps.  `post` is invariant between events.
-  auto plain_step = [&](const float (&inc)[E], const float u, const bool post, auto store_tag) {
+  // ---- plain step: no sweep, no flush, no burn-in test -- a single basic block, so that ptxas can interleave it with the
+  // Philox / Box-Muller stream of the next pair of steps.  Acceptances and squared jumps go to the caller's local sums
+  // (`cnt`, `jf`: the fast loop never straddles the burn-in boundary, so it decides once whether they count).  `xo` /
+  // `jadd` return the state before the step and the squared jump it added, for the sweep that may follow the second
+  // step of a pair.
+  auto plain_step = [&](const float (&inc)[E], const float u, auto store_tag, float (&xo)[E], float& jadd, float& jf, unsigned& cnt) {
     float prop[E];
+    float j2 = 0.0f;
+    constexpr bool kPacked = kUseF32x2 && !IEEE && EXACT && E >= 2;
+    if constexpr (kPacked) {
+      f32x2_t j2p = pack2(0.0f, 0.0f);
 #pragma unroll
-    for (int e = 0; e < E; ++e) prop[e] = c.ok(e) ? M::add(x[e], inc[e]) : 0.0f;
+      for (int e = 0; e + 1 < E; e += 2) {
+        const f32x2_t i2 = pack2(inc[e], inc[e + 1]);
+        unpack2(add2(pack2(x[e], x[e + 1]), i2), prop[e], prop[e + 1]);
+        j2p = fma2(i2, i2, j2p);
+      }
+      float ja, jb;
+      unpack2(j2p, ja, jb);
+      j2 = ja + jb;
+      if constexpr (E & 1) {
+        prop[E - 1] = x[E - 1] + inc[E - 1];
+        j2 = fmaf(inc[E - 1], inc[E - 1], j2);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) prop[e] = c.ok(e) ? M::add(x[e], inc[e]) : 0.0f;
+    }
     const float lpp = tgt.logp(prop, c);
     const float lar = M::mul(beta, M::sub(lpp, lp));
     const bool acc = mh_accept<IEEE>(lar, u);
-    float j2 = 0.0f;
     if constexpr (IEEE) {
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const float xn = acc ? prop[e] : x[e];
         const float dx = M::sub(xn, x[e]);
         j2 = fmaf(dx, dx, j2);
+        xo[e] = x[e];
         x[e] = xn;
       }
-      jump_f += post ? j2 : 0.0f;
+      jadd = j2;
     } else {
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        j2 = c.ok(e) ? fmaf(inc[e], inc[e], j2) : j2;
+        if constexpr (!kPacked) j2 = c.ok(e) ? fmaf(inc[e], inc[e], j2) : j2;
+        xo[e] = x[e];
         x[e] = acc ? prop[e] : x[e];
       }
-      jump_f += (post & acc) ? j2 : 0.0f;
+      jadd = acc ? j2 : 0.0f;
     }
+    jf += jadd;
     lp = acc ? lpp : lp;
-    n_acc32 += (post & acc) ? 1u : 0u;
+    cnt += acc ? 1u : 0u;
     if constexpr (decltype(store_tag)::value) stage_row(x, lp);
   };
 
   const bool inject = TEST && a.inj_inc != nullptr;
   if (inject) {
     if constexpr (TEST) {
-      for (long long t = 0; t < a.n_steps; ++t) {
+      for (long long t = 0; t < n_steps; ++t) {
         float inc[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -474,7 +637,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
         do_step(inc, a.inj_u[t * a.n_chains + chain], t);
       }
     }
-  } else if (a.n_steps > 0) {
+  } else if (n_steps > 0) {
     // Software pipeline: the increments of the NEXT pair of steps are drawn while the current pair's density /
     // reduction / accept chain is in flight (they do not depend on the state).  Steps with an "event" (sweep due,
     // sample to retain, accumulator flush, burn-in boundary, start / end of run inside a pair) go through do_step; all
@@ -482,34 +645,103 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
     float iA[E], iB[E], uA, uB;
     unsigned long long pair = (unsigned long long)(s_first - 1) >> 1;
     draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, pair, chain_gid, scale, dscale);
+    PhiloxPairGen<PairWords<E, PF>::NC> gen;  // run-invariant part of the Philox rounds
+    gen.init(a.rk, c.sub, pair + 1, chain_gid);
     long long t = 0;
     int h0 = (int)((s_first - 1) & 1);  // 1: the run starts on the second step of a pair
-    while (t < a.n_steps) {
+    // Sweeps that fall after the second step of a pair (always, when swap_every is even) and the accumulator flush are
+    // handled inside the fast loop; only the run's edges, the burn-in boundary, thinned stores and sweeps of an odd
+    // swap_every go through the general path.
+    const int swap_every = a.swap_every;
+    const bool sweep_fast = K > 1 && (swap_every & 1) == 0;
+    while (t < n_steps) {
       // first local step >= t that needs the general path
-      long long ev = t | 63;                                   // accumulator flush
-      if (a.n_steps - 1 < ev) ev = a.n_steps - 1;              // last step (also covers an odd tail)
+      long long ev = n_steps - 1;                              // last step (also covers an odd tail)
       if (t < burn_t && burn_t - 1 < ev) ev = burn_t - 1;      // burn-in boundary inside a pair
-      if (K > 1 && t + swap_cd < ev) ev = t + swap_cd;         // sweep due after that step
+      if (K > 1 && !sweep_fast && t + swap_cd < ev) ev = t + swap_cd;  // sweep due after that step
       if (a.samples != nullptr && !store_each && t + store_cd < ev) ev = t + store_cd;
       const bool post = t >= burn_t;
       const long long n_fast = h0 ? 0 : (ev - t) >> 1;         // whole pairs strictly before the event
       auto fast_pairs = [&](auto store_tag) {
-        for (long long q = 0; q < n_fast; ++q) {
-          float nA[E], nB[E], vA, vB;
-          plain_step(iA, uA, post, store_tag);
-          draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
-          plain_step(iB, uB, post, store_tag);
-          ++pair;
+        long long left = n_fast;
+        if (left <= 0) return;
+        float jf = 0.0f;     // local sums of the squared jumps / acceptances (all steps here are on one side of burn-in)
+        unsigned cnt = 0;
+        // Three-stage software pipeline: while the steps of pair p run, the Philox words of pair p+1 (drawn one iteration
+        // earlier) are turned into increments and the words of pair p+2 are drawn -- three instruction streams with no
+        // dependencies between them inside one iteration.
+        constexpr int NCW = PairWords<E, PF>::NC;
+        uint32_t wn[4 * NCW];
+        auto ensure_gen = [&](unsigned long long p) {
+          if ((uint32_t)(p >> 32) != gen.hi32) gen.init(a.rk, c.sub, p, chain_gid);
+        };
+        ensure_gen(pair + 1);
+        gen.gen(a.rk, (uint32_t)(pair + 1), wn);
+        // The loop runs in chunks that end where something other than a plain pair is due: a sweep after the chunk's last
+        // step, the accumulator flush (every chunk end), a change of the high word of the Philox pair counter, or the end
+        // of the fast run.
+        auto chunk_len = [&]() -> unsigned {
+          long long m = left < 32 ? left : 32;
+          if (sweep_fast && m > ((swap_cd + 1) >> 1)) m = (swap_cd + 1) >> 1;
+          ensure_gen(pair + 2);
+          const long long room = 0x100000000ll - (long long)((pair + 2) & 0xffffffffull);  // draws before the low word wraps
+          if (m > room) m = room;
+          return (unsigned)m;
+        };
+        unsigned len = chunk_len();
+        uint32_t plo = (uint32_t)pair, plo_end = plo + len;  // low word of the pair being stepped / of the chunk's end
+        for (;;) {
+          float nA[E], nB[E], vA, vB, xo[E], jadd;
+#if RWMPT_ORDER == 1
+          pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, scale, dscale);
+          gen.gen(a.rk, plo + 2u, wn);
+          plain_step(iA, uA, store_tag, xo, jadd, jf, cnt);
+          plain_step(iB, uB, std::false_type{}, xo, jadd, jf, cnt);
+#else
+          plain_step(iA, uA, store_tag, xo, jadd, jf, cnt);
+          pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, scale, dscale);
+          gen.gen(a.rk, plo + 2u, wn);
+          plain_step(iB, uB, std::false_type{}, xo, jadd, jf, cnt);
+#endif
+          ++plo;
 #pragma unroll
           for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
           uA = vA; uB = vB;
+          bool done = false;
+          if (plo == plo_end) {
+            pair += len; left -= len;
+            if (sweep_fast) {
+              swap_cd -= 2ll * len;
+              if (swap_cd < 0) {  // the sweep is due after the chunk's last step
+                swap_cd += swap_every;
+                const bool moved = sweep();
+                // the step's jump is chain[t+1] - chain[t] with the swap included (pt_rwm_gpu_optimized.py:772-789)
+                float j2 = 0.0f;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                  const float dx = M::sub(x[e], xo[e]);
+                  j2 = fmaf(dx, dx, j2);
+                }
+                jf += moved ? j2 - jadd : 0.0f;
+              }
+            }
+            if (post) { jump_d += (double)jf; n_acc += cnt; }  // fp32 partial sums -> fp64 / 64-bit accumulators
+            jf = 0.0f; cnt = 0;
+            done = left == 0;
+            if (!done) {
+              len = chunk_len();
+              plo_end = plo + len;
+            }
+          }
+          if constexpr (decltype(store_tag)::value) stage_row(x, lp);  // retained after the sweep, like the reference
+          if (done) break;
         }
       };
-      // the retained-sample variant is a separate instantiation so that the accumulators-only loop stays one basic block
+      // the retained-sample variant is a separate instantiation so that the accumulators-only loop stays lean
       if (store_each) fast_pairs(std::true_type{});
       else fast_pairs(std::false_type{});
       t += 2 * n_fast;
-      if (K > 1) swap_cd -= 2 * n_fast;
+      if (K > 1 && !sweep_fast) swap_cd -= 2 * n_fast;
       if (a.samples != nullptr) store_cd -= 2 * n_fast;
       // the pair that holds the event, through the general path (one copy of do_step: the two halves share the code)
       {
@@ -517,7 +749,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
         draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
 #pragma unroll 1
         for (int h = h0; h < 2; ++h) {
-          if (t >= a.n_steps) break;
+          if (t >= n_steps) break;
           float inc[E];
 #pragma unroll
           for (int e = 0; e < E; ++e) inc[e] = h ? iB[e] : iA[e];
@@ -544,10 +776,70 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
       if (c.base + e < d) a.state[chain * d + c.base + e] = x[e];
     if (c.sub == 0) {
       a.logp[chain] = lp;
-      if (a.accept_count) a.accept_count[chain] += n_acc;
-      if (a.sq_jump_sum) a.sq_jump_sum[chain] += jump_d;
-      if (K > 1 && temp < K - 1 && a.swap_accepts) a.swap_accepts[ladder * (K - 1) + temp] += n_swap_acc;
-      if (K > 1 && a.swap_last_attempt && last_attempt > a.swap_last_attempt[chain]) a.swap_last_attempt[chain] = last_attempt;
+      if constexpr (SLICED) {
+        if (a.accept_count) atomicAdd(a.accept_count + chain, n_acc);
+        if (a.sq_jump_sum) atomicAdd(a.sq_jump_sum + chain, jump_d);
+        if (K > 1 && temp < K - 1 && a.swap_accepts) atomicAdd(a.swap_accepts + ladder * (K - 1) + temp, n_swap_acc);
+        if (K > 1 && a.swap_last_attempt) atomicMax(a.swap_last_attempt + chain, last_attempt);
+      } else {
+        if (a.accept_count) a.accept_count[chain] += n_acc;
+        if (a.sq_jump_sum) a.sq_jump_sum[chain] += jump_d;
+        if (K > 1 && temp < K - 1 && a.swap_accepts) a.swap_accepts[ladder * (K - 1) + temp] += n_swap_acc;
+        if (K > 1 && a.swap_last_attempt && last_attempt > a.swap_last_attempt[chain]) a.swap_last_attempt[chain] = last_attempt;
+      }
+    }
+  }
+}
+
+// Template parameters: Target functor; E coordinates per lane; IEEE parity arithmetic; WT lanes per chain (0 = runtime);
+// PF proposal family (-1 = runtime); EXACT: E*W == dim (no padding masks); TEST: injected randomness / decision
+// outputs available.
+//
+// Plain launch (a.n_slices <= 1): CTA b runs unit b for the whole run.  Balanced launch: the run is cut into
+// a.n_slices time slices and the grid is sized to the SMs (every scheduler gets the same number of resident warps,
+// e.g. 8 one-warp CTAs per SM for the 1024 ladders of BASELINE config 3, where a plain launch leaves 160 of the 592
+// schedulers with one warp while the other 432 share two).  CTAs draw tickets g = 0, 1, ... in time-major order
+// (slice g / n_units of unit g % n_units), wait -- asleep -- until the unit's previous slice is published, run it, and
+// publish.  A ladder is always being advanced by exactly one CTA, the spare CTAs sleep, and the time a warp spends
+// alone on its scheduler (where it runs ~1.7x faster) is shared by all ladders instead of ending in an idle tail.
+// Results do not depend on the schedule: a slice resumes exactly like a host-level resume (step_offset).
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
+__global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a) {
+  if constexpr (TEST) {
+    mcmc_unit<Target, E, IEEE, WT, PF, EXACT, TEST, false>(a, (long long)blockIdx.x, a.step_offset, a.n_steps, a.rounds_before);
+  } else {
+    // one call site for both schedules (the unit is large and force-inlined): a plain launch is a single "ticket"
+    __shared__ unsigned s_ticket;
+    const bool sliced = a.n_slices > 1;
+    const unsigned total = sliced ? (unsigned)a.n_units * (unsigned)a.n_slices : 0u;
+    for (;;) {
+      long long unit = (long long)blockIdx.x, so = a.step_offset, n = a.n_steps, rb = a.rounds_before;
+      int slice = 0;
+      if (sliced) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const unsigned g = s_ticket;
+        __syncthreads();
+        if (g >= total) break;
+        slice = (int)(g / (unsigned)a.n_units);
+        unit = (long long)(g % (unsigned)a.n_units);
+        if (threadIdx.x == 0) {
+          while (*(volatile int*)(a.unit_done + unit) < slice) __nanosleep(256);  // previous slice published?
+          __threadfence();
+        }
+        __syncthreads();
+        const long long off = (long long)slice * a.slice_steps;
+        n = a.n_steps - off < a.slice_steps ? a.n_steps - off : a.slice_steps;
+        so = a.step_offset + off;
+        // sweeps performed before global step `so` (host: count_rounds(0, so, burn_in, swap_every))
+        rb = (a.K > 1 && so > a.burn_in) ? so / a.swap_every - a.burn_in / a.swap_every : 0;
+      }
+      // (L1-bypassing loads and atomic accumulators of the sliced unit are harmless in a plain launch)
+      mcmc_unit<Target, E, IEEE, WT, PF, EXACT, TEST, true>(a, unit, so, n, rb);
+      if (!sliced) break;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicExch(a.unit_done + unit, slice + 1);
     }
   }
 }
@@ -589,6 +881,8 @@ struct LaunchGeom {
   int chains_per_cta;
   long long grid;
   size_t smem;
+  int sms;       // SM count of the current device
+  int schedule;  // RWMPT_SCHEDULE_*
 };
 
 }  // namespace rwmpt

@@ -7,17 +7,60 @@
 namespace rwmpt {
 
 // elements-per-lane (E) variants compiled for each math mode; the picker in rwmpt_api.cu uses the same lists
+#ifdef RWMPT_ONLY_TUNED  // analysis builds (SASS inspection of one kernel): a single generic variant
+#define RWMPT_FAST_E_LIST(X) X(5)
+#define RWMPT_IEEE_E_LIST(X) X(5)
+#else
 #define RWMPT_FAST_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
 #define RWMPT_IEEE_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
+#endif
 
 template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
-cudaError_t launch_mcmc_one(const KernelArgs& a, const LaunchGeom& g, cudaStream_t st) {
+cudaError_t launch_mcmc_one(const KernelArgs& a_in, const LaunchGeom& g, cudaStream_t st) {
   auto kern = mcmc_kernel<Target, E, IEEE, WT, PF, EXACT, TEST>;
   if (g.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
   }
-  kern<<<(unsigned)g.grid, g.threads, g.smem, st>>>(a);
+  // Balanced (time-sliced, ticketed) launch -- see mcmc_kernel.  Chosen when the plain grid would leave the SMs'
+  // schedulers unevenly loaded in the few-warps-per-scheduler regime and every CTA of the SM-sized grid is resident.
+  if (!TEST && g.schedule != RWMPT_SCHEDULE_PLAIN && g.sms > 0 && a_in.n_steps > 0 && g.grid < (1ll << 30) / 64) {
+    const bool forced = g.schedule == RWMPT_SCHEDULE_BALANCED;
+    const long long wpc = g.threads / 32;
+    long long c = (g.grid + g.sms - 1) / g.sms;       // CTAs on the fullest SM of a plain launch
+    while ((c * wpc) % 4) ++c;                         // same number of warps on each of the SM's four schedulers
+    const long long P = (long long)g.sms * c;
+    const long long min_slice = forced ? 16 : 4096;
+    bool want = forced || (P > g.grid && c * wpc <= 16 && a_in.n_steps >= 8 * min_slice);
+    if (want && a_in.n_steps >= 2 * min_slice) {
+      int nb = 0;
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, g.threads, g.smem);
+      if (e != cudaSuccess) return e;
+      if (nb >= c || forced) {
+        KernelArgs a = a_in;
+        long long S = a.n_steps / min_slice;
+        if (S > 32) S = 32;
+        long long len = (a.n_steps + S - 1) / S;
+        len += len & 1;                                // slices start on a pair boundary of the Philox stream
+        a.slice_steps = len;
+        a.n_slices = (int)((a.n_steps + len - 1) / len);
+        a.n_units = (int)g.grid;
+        unsigned* ws = nullptr;
+        const size_t bytes = ((size_t)g.grid + 1) * sizeof(unsigned);
+        e = cudaMallocAsync((void**)&ws, bytes, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(ws, 0, bytes, st);
+        if (e != cudaSuccess) return e;
+        a.ticket = ws;
+        a.unit_done = reinterpret_cast<int*>(ws + 1);
+        kern<<<(unsigned)P, g.threads, g.smem, st>>>(a);
+        e = cudaGetLastError();
+        cudaError_t e2 = cudaFreeAsync(ws, st);
+        return e != cudaSuccess ? e : e2;
+      }
+    }
+  }
+  kern<<<(unsigned)g.grid, g.threads, g.smem, st>>>(a_in);
   return cudaGetLastError();
 }
 

@@ -8,6 +8,8 @@ bit-exact and chain states match (they are x + increment, so exactly) -- a decis
 which moves the log-density by an ulp); log-densities agree to 1e-5 relative.  With the native Philox stream,
 acceptance agrees within 3 Monte-Carlo standard errors and ESJD within 2 %.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -285,8 +287,67 @@ def test_native_rng_matches_reference_statistics(key, d, x, acc_ref, acc_se, esj
     acc_mean, esjd_mean = acc.mean(), esjd.mean()
     acc_err = np.hypot(acc.std(ddof=1) / np.sqrt(len(acc)), acc_se)
     esjd_err = np.hypot(esjd.std(ddof=1) / np.sqrt(len(esjd)), esjd_se)
-    assert abs(acc_mean - acc_ref) <= 3 * acc_err, (acc_mean, acc_ref, acc_err)
+    # The data/ chains are still in their transient at 1e6 steps (tests/golden/make_oracle_transient_stats.py: the NumPy
+    # port of the reference itself drifts from 0.80 at 2e5 steps to 0.727 at 1e6 for d=30), so their seed-to-seed s.e.
+    # understates the uncertainty of the pooled rate: 1.5 % relative slack on top of the 3 s.e.
+    assert abs(acc_mean - acc_ref) <= 3 * acc_err + 0.015 * acc_ref, (acc_mean, acc_ref, acc_err)
     assert abs(esjd_mean - esjd_ref) <= 3 * esjd_err + 0.02 * esjd_ref, (esjd_mean, esjd_ref, esjd_err)
+
+
+def test_native_rng_matches_oracle_run_in_transient():
+    """Same configuration as the d=30 data/ point, against a 384-chain 1e6-step run of the NumPy oracle (recorded by
+    tests/golden/make_oracle_transient_stats.py): acceptance within 3 standard errors at 1e6 steps."""
+    import json
+    dev = _cuda()
+    RWM, _ = _algs()
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_even_rosenbrock_d30.json")) as f:
+        rec = json.load(f)
+    ref, ref_se = rec["acceptance_at_steps"]["1000000"]
+    d, x = 30, rec["config"]["x"]
+    np.random.seed(7)
+    algo = RWM(d, x * x / d, product_target("even_rosenbrock_d30"), burn_in=1000, device=dev, num_chains=1024, seed=99)
+    algo.generate_samples(1_000_000)
+    acc = algo.acceptance_rates.cpu().numpy()
+    err = np.hypot(acc.std(ddof=1) / np.sqrt(len(acc)), ref_se)
+    assert abs(acc.mean() - ref) <= 3 * err, (acc.mean(), ref, err)
+
+
+@pytest.mark.parametrize("d,lanes", [(20, 0), (30, 0), (10, 0), (7, 0), (20, 2), (50, 0)])
+def test_native_normal_increments_are_iid(d, lanes):
+    """In-kernel Philox + Box-Muller (scalar and packed-fp32 layouts, every lanes/elements mapping): on a flat target
+    every proposal is accepted, so the stored trajectory's differences ARE the increments.  They must be N(0, var)
+    with no correlation between coordinates, between consecutive steps, or between squared values (two normals that
+    share a Box-Muller radius)."""
+    dev = _cuda()
+    RWM, _ = _algs()
+    import rwm_pt_pytorch_b200.target_distributions as td
+    t = td.ScaledMultivariateNormalTorch(d, scaling_factors=np.full(d, 1e-4, np.float32), device=torch.device("cpu"))
+    var, B, T = 0.25, 64, 4096
+    algo = RWM(d, var, t, burn_in=0, device=dev, num_chains=B, seed=2024, store="all", lanes_per_chain=lanes,
+               initial_states=np.zeros((B, d)))
+    algo.generate_samples(T)
+    assert abs(algo.acceptance_rate - 1.0) < 1e-4
+    x = algo.get_chain_gpu().double().cpu().numpy()           # (B, T+1, d)
+    z = np.diff(x, axis=1) / np.sqrt(var)                      # (B, T, d)
+    n = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(n)
+    assert abs(z.var() - 1.0) < 5 * np.sqrt(2.0 / n) + 1e-4    # + fp32 rounding of x_t - x_{t-1}
+    assert abs((z ** 4).mean() - 3.0) < 5 * np.sqrt(96.0 / n) + 1e-3
+    per_coord = z.reshape(-1, d)
+    m = per_coord.shape[0]
+    assert np.abs(per_coord.mean(0)).max() < 5.5 / np.sqrt(m)
+    assert np.abs(per_coord.var(0) - 1).max() < 5.5 * np.sqrt(2.0 / m) + 1e-4
+    corr = np.corrcoef(per_coord.T)                            # between coordinates of one step
+    assert np.abs(corr - np.eye(d)).max() < 5.5 / np.sqrt(m)
+    corr2 = np.corrcoef((per_coord ** 2).T)                    # shared-radius pairs would show up here
+    assert np.abs(corr2 - np.eye(d)).max() < 5.5 / np.sqrt(m)
+    lag = np.concatenate([z[:, :-1].reshape(-1, d), z[:, 1:].reshape(-1, d)], axis=1)   # step t vs step t+1
+    cl = np.corrcoef(lag.T)[:d, d:]
+    assert np.abs(cl).max() < 5.5 / np.sqrt(lag.shape[0])
+    cl2 = np.corrcoef((lag ** 2).T)[:d, d:]
+    assert np.abs(cl2).max() < 5.5 / np.sqrt(lag.shape[0])
+    across = np.corrcoef(z[:8].transpose(1, 0, 2).reshape(T, -1).T)
+    assert np.abs(across - np.eye(across.shape[0])).max() < 6.0 / np.sqrt(T)
 
 
 @pytest.mark.parametrize("key,d,var,prop", [("rough_carpet_pm4_d20", 20, 1.929231 ** 2 / 20, "normal"),
@@ -511,6 +572,44 @@ def test_resume_equals_single_run_and_sharding_is_invariant():
     h2 = PT(20, 0.9, t, num_ladders=4, chain_id_base=4 * 8, **kw); h2.generate_samples(300)
     assert torch.equal(torch.cat([h1.current_states, h2.current_states]), full.current_states)
     assert full.num_swap_acceptances == h1.num_swap_acceptances + h2.num_swap_acceptances
+
+
+@pytest.mark.parametrize("store", ["none", "cold", "all"])
+def test_balanced_schedule_is_bit_identical_to_plain(store):
+    """The balanced launch (SM-sized grid, time slices handed out by ticket, CTAs handing ladders over through HBM) must
+    give exactly the results of the plain one-CTA-per-ladder launch: states, log-densities, every accumulator and the
+    retained samples."""
+    dev = _cuda()
+    RWM, PT = _algs()
+    t = product_target("rough_carpet_d20")
+    res = []
+    for sched in (1, 2):
+        kw = dict(geom_temp_spacing=True, swap_every=10, burn_in=40, device=dev, store=store, seed=5, num_ladders=37)
+        if store != "none":
+            kw["pre_allocate_steps"] = 1000
+        p = PT(20, 0.9, t, **kw)
+        p._batch.schedule = sched
+        p.generate_samples(1000)
+        b = p._batch
+        res.append((p.current_states.clone(), b.logp.clone(), b.accept_count.clone(), b.sq_jump_sum.clone(),
+                    b.swap_accepts.clone(), b.swap_last_attempt.clone(), None if b.samples is None else b.samples.clone()))
+    for u, v in zip(*res):
+        if u is None:
+            continue
+        if u.dtype == torch.float64:   # squared-jump sums: fp32 partial sums reach the fp64 accumulator at slice ends too
+            torch.testing.assert_close(u, v, rtol=1e-6, atol=0)
+        else:
+            assert torch.equal(u, v)
+    # RWM, odd chain count (partial CTA), odd step count
+    out = []
+    for sched in (1, 2):
+        r = RWM(20, 0.4, t, burn_in=51, device=dev, num_chains=203, store="none", seed=77)
+        r._ensure_batch(1)
+        r._batch.schedule = sched
+        r._batch.run(777); r._refresh_stats()
+        out.append((r.current_state.clone(), r._batch.accept_count.clone(), r._batch.sq_jump_sum.clone()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    torch.testing.assert_close(out[0][2], out[1][2], rtol=1e-6, atol=0)
 
 
 def test_step_api_and_reference_bookkeeping():
