@@ -154,12 +154,16 @@ struct PhiloxPairGen {
 
 template <int E, bool IEEE, int PF, class C>
 __device__ __forceinline__ void pair_transform(const KernelArgs& a, const C& c, const uint32_t (&w)[4 * PairWords<E, PF>::NC],
-                                               float (&incA)[E], float (&incB)[E], float& uA, float& uB, float scale,
-                                               const float (&dscale)[E]) {
+                                               float (&incA)[E], float (&incB)[E], float& uA, float& uB, uint32_t& sA,
+                                               uint32_t& sB, float scale, const float (&dscale)[E]) {
   constexpr int NC = PairWords<E, PF>::NC;
   const int pf = PF >= 0 ? PF : a.prop_family;
   uA = from_leader(u01_from_bits(w[4 * NC - 1]), c);
   uB = from_leader(u01_from_bits(w[4 * NC - 2]), c);
+  // Only the leader lane's two accept words are consumed; the same words of the chain's second lane feed the swap sweep
+  // that may follow step A / step B (see `sweep`), so a sweep costs no Philox call of its own.
+  sA = w[4 * NC - 1];
+  sB = w[4 * NC - 2];
   if constexpr (!IEEE) {  // fast path compares ln(u) < lar (see mh_accept)
     uA = lg2_approx(uA) * kLn2;
     uB = lg2_approx(uB) * kLn2;
@@ -242,21 +246,11 @@ __device__ __forceinline__ void pair_transform(const KernelArgs& a, const C& c, 
 
 template <int E, bool IEEE, int PF, class C>
 __device__ __forceinline__ void draw_pair(const KernelArgs& a, const C& c, float (&incA)[E], float (&incB)[E], float& uA,
-                                          float& uB, unsigned long long pair, unsigned long long chain_gid, float scale,
-                                          const float (&dscale)[E]) {
+                                          float& uB, uint32_t& sA, uint32_t& sB, unsigned long long pair,
+                                          unsigned long long chain_gid, float scale, const float (&dscale)[E]) {
   PairWords<E, PF> pw;
   pw.full(a.rk, c.sub, pair, chain_gid);
-  pair_transform<E, IEEE, PF>(a, c, pw.w, incA, incB, uA, uB, scale, dscale);
-}
-
-// same words through the run-invariant partial evaluation (the caller keeps gen.hi32 == pair >> 32)
-template <int E, bool IEEE, int PF, class C>
-__device__ __forceinline__ void draw_pair_fast(const KernelArgs& a, const C& c, const PhiloxPairGen<PairWords<E, PF>::NC>& gen,
-                                               float (&incA)[E], float (&incB)[E], float& uA, float& uB, uint32_t pair_lo,
-                                               float scale, const float (&dscale)[E]) {
-  uint32_t w[4 * PairWords<E, PF>::NC];
-  gen.gen(a.rk, pair_lo, w);
-  pair_transform<E, IEEE, PF>(a, c, w, incA, incB, uA, uB, scale, dscale);
+  pair_transform<E, IEEE, PF>(a, c, pw.w, incA, incB, uA, uB, sA, sB, scale, dscale);
 }
 
 // One uniform per (ladder, sweep, pair) on a separate Philox key.
@@ -419,17 +413,24 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
 
   // ---- adjacent-temperature sweep of the CTA's ladders (pt_rwm_gpu_optimized.py:594-633); returns whether this
   // thread's chain received a new state ------------------------------------------------------------------------
-  auto sweep = [&]() -> bool {
+  // `spare`: this lane's unused accept word of the step the sweep follows (pair_transform).
+  auto sweep = [&](const uint32_t spare) -> bool {
     bool changed = false;
     if (warp_ladder && a.swap_mode == RWMPT_SWAP_REFERENCE) {
       // reference semantics (pt_rwm_gpu_optimized.py:594-633 with the copy k -> j of :50-59): pair j only rewrites
       // slot j, from the PRE-sweep occupant of slot j+1 -- every pair decides at once on the pre-sweep values.
+      // The pair's uniform is the spare accept word of the colder chain's second lane (its own Philox call when a
+      // chain has a single lane).
       const unsigned long long round_g = (unsigned long long)(rounds_before + round_local);  // 0-based
-      const long long su_base = (round_local * a.n_ladders + ladder) * (K - 1);
       const bool has_next = valid && temp < K - 1;
       float us;
-      if (TEST && a.inj_su != nullptr) us = has_next ? a.inj_su[su_base + temp] : 2.0f;
-      else us = swap_uniform(a.key0, a.key1, ladder_gid, round_g, temp);
+      if constexpr (TEST) {
+        const long long su_base = (round_local * a.n_ladders + ladder) * (K - 1);
+        if (a.inj_su != nullptr) us = has_next ? a.inj_su[su_base + temp] : 2.0f;
+        else us = W >= 2 ? u01_from_bits(__shfl_sync(kFull, spare, c.leader + 1)) : swap_uniform(a.key0, a.key1, ladder_gid, round_g, temp);
+      } else {
+        us = W >= 2 ? u01_from_bits(__shfl_sync(kFull, spare, c.leader + 1)) : swap_uniform(a.key0, a.key1, ladder_gid, round_g, temp);
+      }
       const float lp_n = __shfl_down_sync(kFull, lp, W);
       float xn[E];
 #pragma unroll
@@ -438,7 +439,9 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
 #pragma unroll
       for (int e = 0; e < E; ++e) x[e] = ok ? xn[e] : x[e];
       lp = ok ? lp_n : lp;
-      if (TEST && lead && a.swap_dec && has_next) a.swap_dec[su_base + temp] = ok ? 1 : 0;
+      if constexpr (TEST) {
+        if (lead && a.swap_dec && has_next) a.swap_dec[(round_local * a.n_ladders + ladder) * (K - 1) + temp] = ok ? 1 : 0;
+      }
       n_swap_acc += ok ? 1ull : 0ull;
       last_attempt = ok ? round_g * (unsigned long long)(K - 1) + temp + 1 : last_attempt;
       round_local++;
@@ -501,7 +504,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   };
 
   // ---- one Metropolis step (+ sweep, accumulators, retained sample) with the given increments -----------------
-  auto do_step = [&](const float (&inc)[E], const float u, const long long t) {
+  auto do_step = [&](const float (&inc)[E], const float u, const long long t, const uint32_t spare) {
     // 2. proposal, 3. its log-density
     float prop[E];
 #pragma unroll
@@ -528,7 +531,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
       if (swap_cd == 0) {
         swap_cd = a.swap_every;
         swapped_now = true;
-        sweep();
+        sweep(spare);
       }
       swap_cd--;
     }
@@ -634,7 +637,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
           const int i = c.base + e;
           inc[e] = (i < d) ? a.inj_inc[(t * a.n_chains + chain) * d + i] : 0.0f;
         }
-        do_step(inc, a.inj_u[t * a.n_chains + chain], t);
+        do_step(inc, a.inj_u[t * a.n_chains + chain], t, 0u);
       }
     }
   } else if (n_steps > 0) {
@@ -643,8 +646,9 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
     // sample to retain, accumulator flush, burn-in boundary, start / end of run inside a pair) go through do_step; all
     // other pairs run plain_step twice with no branch at all.
     float iA[E], iB[E], uA, uB;
+    uint32_t sA, sB;  // spare accept words of the current pair (swap uniforms)
     unsigned long long pair = (unsigned long long)(s_first - 1) >> 1;
-    draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, pair, chain_gid, scale, dscale);
+    draw_pair<E, IEEE, PF>(a, c, iA, iB, uA, uB, sA, sB, pair, chain_gid, scale, dscale);
     PhiloxPairGen<PairWords<E, PF>::NC> gen;  // run-invariant part of the Philox rounds
     gen.init(a.rk, c.sub, pair + 1, chain_gid);
     long long t = 0;
@@ -662,8 +666,9 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
       if (a.samples != nullptr && !store_each && t + store_cd < ev) ev = t + store_cd;
       const bool post = t >= burn_t;
       const long long n_fast = h0 ? 0 : (ev - t) >> 1;         // whole pairs strictly before the event
+      long long n_done = 0;                                    // pairs the fast loop ran (at most 2^30 per entry)
       auto fast_pairs = [&](auto store_tag) {
-        long long left = n_fast;
+        const long long left = n_fast;
         if (left <= 0) return;
         float jf = 0.0f;     // local sums of the squared jumps / acceptances (all steps here are on one side of burn-in)
         unsigned cnt = 0;
@@ -680,26 +685,34 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
         // The loop runs in chunks that end where something other than a plain pair is due: a sweep after the chunk's last
         // step, the accumulator flush (every chunk end), a change of the high word of the Philox pair counter, or the end
         // of the fast run.
-        auto chunk_len = [&]() -> unsigned {
-          long long m = left < 32 ? left : 32;
-          if (sweep_fast && m > ((swap_cd + 1) >> 1)) m = (swap_cd + 1) >> 1;
-          ensure_gen(pair + 2);
-          const long long room = 0x100000000ll - (long long)((pair + 2) & 0xffffffffull);  // draws before the low word wraps
-          if (m > room) m = room;
-          return (unsigned)m;
+        // (all 32-bit: `left`, `swap_cd` and the Philox low word; the outer loop re-enters for longer runs)
+        int left32 = (int)(left < (1ll << 30) ? left : (1ll << 30));
+        const int n_here = left32;
+        // pairs up to and including the pair the next sweep follows (tracked here only if it can fall inside this entry)
+        const bool sw_tracked = sweep_fast && ((swap_cd + 1) >> 1) <= (1ll << 30);
+        int sw = sw_tracked ? (int)((swap_cd + 1) >> 1) : 0x7fffffff;
+        uint32_t plo = (uint32_t)pair, plo_end;  // low word of the pair being stepped / of the chunk's end
+        auto chunk_len = [&]() -> int {
+          int m = left32 < 32 ? left32 : 32;
+          m = m < sw ? m : sw;
+          const uint32_t room = 0u - (plo + 2u);   // draws before the low word of the Philox counter wraps (0: a full 2^32)
+          if (room != 0u && (uint32_t)m > room) m = (int)room;
+          return m;
         };
-        unsigned len = chunk_len();
-        uint32_t plo = (uint32_t)pair, plo_end = plo + len;  // low word of the pair being stepped / of the chunk's end
+        ensure_gen(pair + 2);
+        int len = chunk_len();
+        plo_end = plo + (uint32_t)len;
         for (;;) {
           float nA[E], nB[E], vA, vB, xo[E], jadd;
+          uint32_t tA, tB;
 #if RWMPT_ORDER == 1
-          pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, scale, dscale);
+          pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, tA, tB, scale, dscale);
           gen.gen(a.rk, plo + 2u, wn);
           plain_step(iA, uA, store_tag, xo, jadd, jf, cnt);
           plain_step(iB, uB, std::false_type{}, xo, jadd, jf, cnt);
 #else
           plain_step(iA, uA, store_tag, xo, jadd, jf, cnt);
-          pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, scale, dscale);
+          pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, tA, tB, scale, dscale);
           gen.gen(a.rk, plo + 2u, wn);
           plain_step(iB, uB, std::false_type{}, xo, jadd, jf, cnt);
 #endif
@@ -707,53 +720,57 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
 #pragma unroll
           for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
           uA = vA; uB = vB;
+          const uint32_t spareB = sB;
+          sA = tA; sB = tB;
           bool done = false;
           if (plo == plo_end) {
-            pair += len; left -= len;
-            if (sweep_fast) {
-              swap_cd -= 2ll * len;
-              if (swap_cd < 0) {  // the sweep is due after the chunk's last step
-                swap_cd += swap_every;
-                const bool moved = sweep();
-                // the step's jump is chain[t+1] - chain[t] with the swap included (pt_rwm_gpu_optimized.py:772-789)
-                float j2 = 0.0f;
+            pair += (unsigned)len; left32 -= len; sw -= len;
+            if (sw == 0) {  // the sweep is due after the chunk's last step
+              sw = swap_every >> 1;
+              const bool moved = sweep(spareB);
+              // the step's jump is chain[t+1] - chain[t] with the swap included (pt_rwm_gpu_optimized.py:772-789)
+              float j2 = 0.0f;
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                  const float dx = M::sub(x[e], xo[e]);
-                  j2 = fmaf(dx, dx, j2);
-                }
-                jf += moved ? j2 - jadd : 0.0f;
+              for (int e = 0; e < E; ++e) {
+                const float dx = M::sub(x[e], xo[e]);
+                j2 = fmaf(dx, dx, j2);
               }
+              jf += moved ? j2 - jadd : 0.0f;
             }
             if (post) { jump_d += (double)jf; n_acc += cnt; }  // fp32 partial sums -> fp64 / 64-bit accumulators
             jf = 0.0f; cnt = 0;
-            done = left == 0;
+            done = left32 == 0;
             if (!done) {
+              if (plo + 2u < 2u) ensure_gen(pair + 2);  // the low word of the next draw wrapped
               len = chunk_len();
-              plo_end = plo + len;
+              plo_end = plo + (uint32_t)len;
             }
           }
           if constexpr (decltype(store_tag)::value) stage_row(x, lp);  // retained after the sweep, like the reference
           if (done) break;
         }
+        n_done = n_here;
+        if (sweep_fast) swap_cd = sw_tracked ? 2ll * sw - 1 : swap_cd - 2ll * n_here;
       };
       // the retained-sample variant is a separate instantiation so that the accumulators-only loop stays lean
       if (store_each) fast_pairs(std::true_type{});
       else fast_pairs(std::false_type{});
-      t += 2 * n_fast;
-      if (K > 1 && !sweep_fast) swap_cd -= 2 * n_fast;
-      if (a.samples != nullptr) store_cd -= 2 * n_fast;
+      t += 2 * n_done;
+      if (K > 1 && !sweep_fast) swap_cd -= 2 * n_done;
+      if (a.samples != nullptr) store_cd -= 2 * n_done;
+      if (n_done < n_fast) continue;                           // more than 2^30 pairs: re-enter the fast loop
       // the pair that holds the event, through the general path (one copy of do_step: the two halves share the code)
       {
         float nA[E], nB[E], vA, vB;
-        draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, pair + 1, chain_gid, scale, dscale);
+        uint32_t tA, tB;
+        draw_pair<E, IEEE, PF>(a, c, nA, nB, vA, vB, tA, tB, pair + 1, chain_gid, scale, dscale);
 #pragma unroll 1
         for (int h = h0; h < 2; ++h) {
           if (t >= n_steps) break;
           float inc[E];
 #pragma unroll
           for (int e = 0; e < E; ++e) inc[e] = h ? iB[e] : iA[e];
-          do_step(inc, h ? uB : uA, t);
+          do_step(inc, h ? uB : uA, t, h ? sB : sA);
           ++t;
         }
         h0 = 0;
@@ -761,6 +778,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
 #pragma unroll
         for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
         uA = vA; uB = vB;
+        sA = tA; sB = tB;
       }
     }
   }

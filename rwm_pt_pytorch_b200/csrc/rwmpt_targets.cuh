@@ -63,8 +63,8 @@ struct RoughCarpetT {
       // work in base 2.  t_k = h xs^2 + b_k xs + c_k (h = -log2(e)/2, b_k = log2(e) m_k, c_k = h m_k^2 + a_k): the
       // quadratic term is common to the three modes, so logsumexp_k t_k = h xs^2 + logsumexp_k (b_k xs + c_k);
       // and sum_i log2(S_i) = log2(prod_i S_i): one lg2 per lane instead of one per coordinate.
-      // Sums / products are combined as trees (two accumulators) to shorten the dependent chain.  (RWMPT_RC_EXP2: the
-      // largest term is exactly 2^0, so two ex2 + min/mid arithmetic instead of three ex2 -- fewer SFU ops, more issue slots.)
+      // Sums / products are combined as trees (two accumulators) to shorten the dependent chain.  The largest term is exactly
+      // 2^0, so two ex2 (smallest and middle exponent) instead of three; -DRWMPT_RC_EXP3 restores the three-ex2 form.
 #ifndef RWMPT_NO_F32X2
       if constexpr (C::EXACT && E >= 2) {
         // packed fp32: coordinates (e, e+1) share every FFMA2 / FADD2 / FMUL2; max and ex2 stay scalar
@@ -82,7 +82,7 @@ struct RoughCarpetT {
           float d0a, d0b, d1a, d1b, d2a, d2b;
           const f32x2_t d0 = sub2(l0, mx2), d1 = sub2(l1, mx2), d2 = sub2(l2, mx2);
           unpack2(d0, d0a, d0b); unpack2(d1, d1a, d1b); unpack2(d2, d2a, d2b);
-#ifdef RWMPT_RC_EXP2
+#ifndef RWMPT_RC_EXP3
           // the largest term is exactly 2^0: two ex2 (smallest and middle exponent) instead of three
           const f32x2_t lo2 = pack2(fminf(fminf(d0a, d1a), d2a), fminf(fminf(d0b, d1b), d2b));
           float mda, mdb, loa, lob;
@@ -104,7 +104,7 @@ struct RoughCarpetT {
           const float xs = SCALED ? x[E - 1] * s[E - 1] : x[E - 1];
           const float l0 = fmaf(b0, xs, c0), l1 = fmaf(b1, xs, c1), l2 = fmaf(b2, xs, c2);
           const float mx = fmaxf(fmaxf(l0, l1), l2);
-#ifdef RWMPT_RC_EXP2
+#ifndef RWMPT_RC_EXP3
           const float lo = fminf(fminf(l0, l1), l2);
           const float mid = ((l0 + l1) + l2) - (mx + lo);
           const float ss = (1.0f + ex2_approx(mid - mx)) + ex2_approx(lo - mx);
@@ -126,7 +126,7 @@ struct RoughCarpetT {
         const float xs = SCALED ? x[e] * s[e] : x[e];
         const float l0 = fmaf(b0, xs, c0), l1 = fmaf(b1, xs, c1), l2 = fmaf(b2, xs, c2);
         const float mx = fmaxf(fmaxf(l0, l1), l2);
-#ifdef RWMPT_RC_EXP2
+#ifndef RWMPT_RC_EXP3
         const float lo = fminf(fminf(l0, l1), l2);
         const float mid = ((l0 + l1) + l2) - (mx + lo);
         const float ss = (1.0f + ex2_approx(mid - mx)) + ex2_approx(lo - mx);
