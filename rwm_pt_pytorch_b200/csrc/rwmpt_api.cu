@@ -639,37 +639,51 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
   e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   int rc = RWMPT_OK;
-  auto stage = [&](const void* host, size_t bytes, bool in, bool out) -> void* {
-    if (!host || bytes == 0 || rc) return nullptr;
+  // one device arena for every staged buffer (a single cudaMalloc / cudaFree per call), 256-byte aligned slices
+  struct Want { const void* host; size_t bytes; bool in, out; void** slot; };
+  std::vector<Want> wants;
+  auto stage = [&](const void* host, size_t bytes, bool in, bool out, void** slot) {
+    *slot = nullptr;
+    if (host && bytes) wants.push_back({host, bytes, in, out, slot});
+  };
+  stage(r->target.params, sizeof(float) * r->target.n_params, true, false, (void**)&a.target.params);
+  stage(r->prop_scale, sizeof(float) * n_chains, true, false, (void**)&a.prop_scale);
+  stage(r->prop_dim_scale, sizeof(float) * d, true, false, (void**)&a.prop_dim_scale);
+  stage(r->beta, sizeof(float) * n_chains, true, false, (void**)&a.beta);
+  stage(r->state, sizeof(float) * n_chains * d, true, true, (void**)&a.state);
+  stage(r->logp, sizeof(float) * n_chains, true, true, (void**)&a.logp);
+  stage(r->samples, sizeof(float) * stored_chains * r->sample_stride * d, false, true, (void**)&a.samples);
+  stage(r->sample_logp, sizeof(float) * stored_chains * r->sample_stride, false, true, (void**)&a.sample_logp);
+  stage(r->accept_count, 8 * n_chains, true, true, (void**)&a.accept_count);
+  stage(r->sq_jump_sum, 8 * n_chains, true, true, (void**)&a.sq_jump_sum);
+  stage(r->swap_accepts, 8 * r->n_ladders * (K > 1 ? K - 1 : 0), true, true, (void**)&a.swap_accepts);
+  stage(r->swap_last_attempt, 8 * n_chains, true, true, (void**)&a.swap_last_attempt);
+  stage(r->inj_increments, sizeof(float) * r->n_steps * n_chains * d, true, false, (void**)&a.inj_increments);
+  stage(r->inj_uniforms, sizeof(float) * r->n_steps * n_chains, true, false, (void**)&a.inj_uniforms);
+  stage(r->inj_swap_uniforms, sizeof(float) * rounds * r->n_ladders * (K - 1), true, false, (void**)&a.inj_swap_uniforms);
+  stage(r->decisions, (size_t)r->n_steps * n_chains, false, true, (void**)&a.decisions);
+  stage(r->swap_decisions, (size_t)rounds * r->n_ladders * (K > 1 ? K - 1 : 0), false, true, (void**)&a.swap_decisions);
+  size_t total = 0;
+  for (auto& w : wants) total += (w.bytes + 255) & ~(size_t)255;
+  char* arena = nullptr;
+  if (total) {
+    e = cudaMalloc((void**)&arena, total);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc");
+  }
+  size_t off = 0;
+  for (auto& w : wants) {
+    if (rc) break;
     DevBuf b;
-    b.bytes = bytes; b.host = const_cast<void*>(host); b.out = out;
-    cudaError_t ee = cudaMalloc(&b.p, bytes);
-    if (ee != cudaSuccess) { rc = cuda_fail(ee, "cudaMalloc"); return nullptr; }
-    if (in) {
-      ee = cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, st);
-      if (ee != cudaSuccess) rc = cuda_fail(ee, "H2D copy");
-      h2d += bytes;
+    b.p = arena + off; b.bytes = w.bytes; b.host = const_cast<void*>(w.host); b.out = w.out;
+    off += (w.bytes + 255) & ~(size_t)255;
+    *w.slot = b.p;
+    if (w.in) {
+      e = cudaMemcpyAsync(b.p, w.host, w.bytes, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) rc = cuda_fail(e, "H2D copy");
+      h2d += w.bytes;
     }
     bufs.push_back(b);
-    return b.p;
-  };
-  a.target.params = (const float*)stage(r->target.params, sizeof(float) * r->target.n_params, true, false);
-  a.prop_scale = (const float*)stage(r->prop_scale, sizeof(float) * n_chains, true, false);
-  a.prop_dim_scale = (const float*)stage(r->prop_dim_scale, sizeof(float) * d, true, false);
-  a.beta = (const float*)stage(r->beta, sizeof(float) * n_chains, true, false);
-  a.state = (float*)stage(r->state, sizeof(float) * n_chains * d, true, true);
-  a.logp = (float*)stage(r->logp, sizeof(float) * n_chains, true, true);
-  a.samples = (float*)stage(r->samples, sizeof(float) * stored_chains * r->sample_stride * d, false, true);
-  a.sample_logp = (float*)stage(r->sample_logp, sizeof(float) * stored_chains * r->sample_stride, false, true);
-  a.accept_count = (unsigned long long*)stage(r->accept_count, 8 * n_chains, true, true);
-  a.sq_jump_sum = (double*)stage(r->sq_jump_sum, 8 * n_chains, true, true);
-  a.swap_accepts = (unsigned long long*)stage(r->swap_accepts, 8 * r->n_ladders * (K > 1 ? K - 1 : 0), true, true);
-  a.swap_last_attempt = (unsigned long long*)stage(r->swap_last_attempt, 8 * n_chains, true, true);
-  a.inj_increments = (const float*)stage(r->inj_increments, sizeof(float) * r->n_steps * n_chains * d, true, false);
-  a.inj_uniforms = (const float*)stage(r->inj_uniforms, sizeof(float) * r->n_steps * n_chains, true, false);
-  a.inj_swap_uniforms = (const float*)stage(r->inj_swap_uniforms, sizeof(float) * rounds * r->n_ladders * (K - 1), true, false);
-  a.decisions = (unsigned char*)stage(r->decisions, (size_t)r->n_steps * n_chains, false, true);
-  a.swap_decisions = (unsigned char*)stage(r->swap_decisions, (size_t)rounds * r->n_ladders * (K > 1 ? K - 1 : 0), false, true);
+  }
   if (!rc) rc = run_impl(&a, st, false);
   if (!rc) {
     for (auto& b : bufs) {
@@ -681,7 +695,7 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
   }
   e = cudaStreamSynchronize(st);
   if (!rc && e != cudaSuccess) rc = cuda_fail(e, "stream synchronize");
-  for (auto& b : bufs) cudaFree(b.p);
+  if (arena) cudaFree(arena);
   cudaStreamDestroy(st);
   if (h2d_bytes) *h2d_bytes = h2d;
   if (d2h_bytes) *d2h_bytes = d2h;
