@@ -150,6 +150,9 @@ int64_t rwmpt_count_swap_rounds(int64_t step_offset, int64_t n_steps, int64_t bu
 
 /* Which (lanes_per_chain, elements_per_lane) the auto heuristic picks; returns lanes or <0. */
 int rwmpt_pick_lanes(int32_t dim, int32_t n_temps, int64_t n_ladders, int32_t math_mode, int32_t* elems_per_lane);
+/* Same for a full run description (target / proposal family and the lanes_per_chain request included: some BASELINE
+ * workloads have tuned geometries); host arithmetic only. */
+int rwmpt_pick_geometry(const rwmpt_run_args_t* args, int32_t* lanes_per_chain, int32_t* elems_per_lane);
 
 /* Batched target log-density, replaces TorchTargetDistribution.log_density (interfaces/target_torch.py:32-43):
  * out[n] = log pi(x[n, :]). */

@@ -175,6 +175,16 @@ class LadderBatch:
             return dec, (None if sdec is None else sdec[:n_rounds])
         return None
 
+    def geometry(self):
+        """(elements_per_lane, lanes_per_chain) the fast-math launch of this batch uses (`rwmpt_pick_geometry`)."""
+        a = _lib.RunArgs()
+        a.target = self._target_struct()
+        a.proposal_family, a.n_temps, a.n_ladders = self.prop_family, self.K, self.L
+        a.math_mode, a.lanes_per_chain = self.math_mode, self.lanes_per_chain
+        w, e = C.c_int32(), C.c_int32()
+        _lib.check(self.lib.rwmpt_pick_geometry(C.byref(a), C.byref(w), C.byref(e)))
+        return e.value, w.value
+
     # ---- statistics ------------------------------------------------------------------------------------
     def post_burn_in_steps(self) -> int:
         return max(self.total_steps - self.burn_in, 0)

@@ -66,7 +66,7 @@ static int check_target(const rwmpt_target_t* t) {
 // Choose lanes-per-chain W and elements-per-lane E.  Candidates: E from the compiled list, W a power of two,
 // E*W >= d, no lane entirely padding, and the ladder (K*W threads) must fit one CTA.  Prefer the least padding;
 // among equals prefer more lanes while the grid is too small to fill the machine (latency hiding), else fewer.
-static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_W, LaunchGeom* g) {
+static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_W, LaunchGeom* g, int family = -1, int pf = -1) {
   const int* list = ieee ? kIeeeE : kFastE;
   const int n_list = ieee ? (int)(sizeof(kIeeeE) / sizeof(int)) : (int)(sizeof(kFastE) / sizeof(int));
   const long long n_chains = n_ladders * K;
@@ -88,6 +88,13 @@ static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_
       if (score < best_score) { best_score = score; bestE = E; bestW = W; }
       break;  // list is ascending: first E that fits is the least padded for this W
     }
+  }
+  // tuned-only geometry: ThreeMixture d = 50..56 with a Laplace / UniformRadius proposal (BASELINE config 4) runs 7
+  // coordinates x 8 lanes (rwmpt_inst_three_mixture.cu); E = 7 is not in the generic lists
+  if (!ieee && want_W <= 0 && family == RWMPT_T_THREE_MIXTURE && (pf == RWMPT_P_LAPLACE || pf == RWMPT_P_UNIFORM_RADIUS) &&
+      d > 49 && d <= 56 && K * 8 <= kMaxCtaThreads) {
+    bestE = 7;
+    bestW = 8;
   }
   if (bestE < 0)
     return fail(RWMPT_ENOTSUP, "no kernel variant for dim=%d n_temps=%d lanes_per_chain=%d (max dim %d; n_temps*lanes <= %d)",
@@ -180,7 +187,7 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
 
   LaunchGeom g;
   const bool ieee = r->math_mode == RWMPT_MATH_IEEE;
-  rc = pick_geometry(d, r->n_temps, r->n_ladders, ieee, r->lanes_per_chain, &g);
+  rc = pick_geometry(d, r->n_temps, r->n_ladders, ieee, r->lanes_per_chain, &g, r->target.family, r->proposal_family);
   if (rc) return rc;
   if (g.grid > 2147483647LL) return fail(RWMPT_ENOTSUP, "too many CTAs (%lld)", g.grid);
   if (r->schedule < RWMPT_SCHEDULE_AUTO || r->schedule > RWMPT_SCHEDULE_BALANCED)
@@ -435,6 +442,18 @@ int rwmpt_pick_lanes(int32_t dim, int32_t n_temps, int64_t n_ladders, int32_t ma
   if (rc) return rc;
   if (elems_per_lane) *elems_per_lane = g.E;
   return g.W;
+}
+
+int rwmpt_pick_geometry(const rwmpt_run_args_t* r, int32_t* lanes_per_chain, int32_t* elems_per_lane) {
+  if (!r) return fail(RWMPT_EINVAL, "args is NULL");
+  if (r->target.dim < 1 || r->n_temps < 1 || r->n_ladders < 1) return fail(RWMPT_EINVAL, "dim, n_temps, n_ladders must be >= 1");
+  LaunchGeom g;
+  const int rc = pick_geometry(r->target.dim, r->n_temps, r->n_ladders, r->math_mode == RWMPT_MATH_IEEE, r->lanes_per_chain, &g,
+                               r->target.family, r->proposal_family);
+  if (rc) return rc;
+  if (lanes_per_chain) *lanes_per_chain = g.W;
+  if (elems_per_lane) *elems_per_lane = g.E;
+  return RWMPT_OK;
 }
 
 int rwmpt_log_density(const rwmpt_target_t* target, const float* x, int64_t n, float* out, int32_t math_mode,

@@ -168,6 +168,25 @@ __device__ __forceinline__ void pair_transform(const KernelArgs& a, const C& c, 
     uA = lg2_approx(uA) * kLn2;
     uB = lg2_approx(uB) * kLn2;
   }
+  if constexpr (!IEEE) {
+    if (pf == RWMPT_P_LAPLACE) {
+      // laplace.py:47-69 without a conversion or a branch: 23 word bits -> f in [1, 2); r = 2f - 3 = 2u in [-1, 1);
+      // log1p(max(-|r|, -0.999999)) = ln(max(1 - |r|, 1e-6)) <= 0, so the increment is |s ln(.)| with the sign of u.
+      // `dscale` is 0 on padding coordinates (mcmc_unit), which keeps their increment at 0.
+      float sdl[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) sdl[e] = scale * dscale[e] * kLn2;
+#pragma unroll
+      for (int e = 0; e < 2 * E; ++e) {
+        const float f = __uint_as_float((w[e] & 0x007fffffu) | 0x3f800000u);
+        const float r = fmaf(2.0f, f, -3.0f);
+        const float m = lg2_approx(fmaxf(1.0f - fabsf(r), 1e-6f)) * sdl[e < E ? e : e - E];
+        const float v = copysignf(m, r);
+        if (e < E) incA[e] = v; else incB[e - E] = v;
+      }
+      return;
+    }
+  }
   if (pf == RWMPT_P_LAPLACE) {
     // laplace.py:47-69: u in (-.5,.5); -s * sign(u) * log1p(max(-2|u|, -0.999999))
 #pragma unroll
@@ -319,7 +338,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   for (int e = 0; e < E; ++e) {
     const int i = c.base + e;
     x[e] = (i < d) ? (SLICED ? __ldcg(a.state + chain * d + i) : a.state[chain * d + i]) : 0.0f;
-    dscale[e] = (i < d && a.prop_dim_scale) ? a.prop_dim_scale[i] : 1.0f;
+    dscale[e] = i < d ? (a.prop_dim_scale ? a.prop_dim_scale[i] : 1.0f) : 0.0f;  // 0 on padding: Laplace increments stay 0 there
   }
   float lp = SLICED ? __ldcg(a.logp + chain) : a.logp[chain];
   const float beta = a.beta[chain];
@@ -579,7 +598,8 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   auto plain_step = [&](const float (&inc)[E], const float u, auto store_tag, float (&xo)[E], float& jadd, float& jf, unsigned& cnt) {
     float prop[E];
     float j2 = 0.0f;
-    constexpr bool kPacked = kUseF32x2 && !IEEE && EXACT && E >= 2;
+    // (a Laplace increment is exactly 0 on padding coordinates -- see pair_transform -- so x stays 0 there without a mask)
+    constexpr bool kPacked = kUseF32x2 && !IEEE && (EXACT || PF == RWMPT_P_LAPLACE) && E >= 2;
     if constexpr (kPacked) {
       f32x2_t j2p = pack2(0.0f, 0.0f);
 #pragma unroll

@@ -155,8 +155,9 @@ template <int E, bool IEEE>
 struct ThreeMixture {
   using M = Mth<IEEE>;
   float lw[3], c1[3], J;
+  float cst2[3];  // fast path: log2(e) * (c1_k [+ J] + lw_k)
   bool scaled;
-  float mu[3][E];
+  float mu[3][E];  // fast path holds -mu (the centring is one FFMA: x * s - mu)
   float s[E];
 
   template <class C>
@@ -167,41 +168,94 @@ struct ThreeMixture {
     scaled = P[6] != 0.0f;
     J = P[7];
 #pragma unroll
+    for (int k = 0; k < 3; ++k) cst2[k] = kLog2e * ((scaled ? c1[k] + J : c1[k]) + lw[k]);
+#pragma unroll
     for (int e = 0; e < E; ++e) {
       const int i = c.base + e;
       const bool ok = i < c.d;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) mu[k][e] = ok ? P[RWMPT_PARAM_HEADER + k * c.d + i] : 0.0f;
+      for (int k = 0; k < 3; ++k) {
+        const float m = ok ? P[RWMPT_PARAM_HEADER + k * c.d + i] : 0.0f;
+        mu[k][e] = IEEE ? m : -m;
+      }
       s[e] = (ok && scaled) ? P[RWMPT_PARAM_HEADER + 3 * c.d + i] : 1.0f;
     }
   }
 
   template <class C>
   __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
-    float q[3] = {0.0f, 0.0f, 0.0f};
+    if constexpr (!IEEE) {
+      // Padding coordinates hold x = 0 and mu = 0 (callers zero them), so no masks.  Base-2 log-sum-exp of the three
+      // t_k = -q_k / 2 + const_k; adjacent coordinates share packed FFMA2s.
+      float q[3];
+#ifndef RWMPT_NO_F32X2
+      if constexpr (E >= 2) {
+        f32x2_t Q[3] = {pack2(0.0f, 0.0f), pack2(0.0f, 0.0f), pack2(0.0f, 0.0f)};
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const float xs = scaled ? M::mul(x[e], s[e]) : x[e];
-      if (c.ok(e)) {
+        for (int e = 0; e + 1 < E; e += 2) {
+          const f32x2_t X = pack2(x[e], x[e + 1]), S = pack2(s[e], s[e + 1]);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const f32x2_t D = fma2(X, S, pack2(mu[k][e], mu[k][e + 1]));
+            Q[k] = fma2(D, D, Q[k]);
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const float dd = M::sub(xs, mu[k][e]);
-          q[k] = IEEE ? M::add(q[k], M::mul(dd, dd)) : fmaf(dd, dd, q[k]);
+          float qa, qb;
+          unpack2(Q[k], qa, qb);
+          q[k] = qa + qb;
+          if constexpr (E & 1) {
+            const float dd = fmaf(x[E - 1], s[E - 1], mu[k][E - 1]);
+            q[k] = fmaf(dd, dd, q[k]);
+          }
+        }
+      } else
+#endif
+      {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) q[k] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float dd = fmaf(x[e], s[e], mu[k][e]);
+            q[k] = fmaf(dd, dd, q[k]);
+          }
         }
       }
-    }
-    float t[3];
+      float t[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float qq = group_sum(q[k], c);
-      float v = M::add(M::mul(-0.5f, qq), c1[k]);
-      if (scaled) v = M::add(v, J);
-      t[k] = M::add(v, lw[k]);
+      for (int k = 0; k < 3; ++k) t[k] = fmaf(-0.5f * kLog2e, group_sum(q[k], c), cst2[k]);
+      const float mx = fmaxf(fmaxf(fmaxf(t[0], t[1]), t[2]), -3.0e38f);  // all -inf (overflowed state) -> -inf, not NaN
+      const float ss = (ex2_approx(t[0] - mx) + ex2_approx(t[1] - mx)) + ex2_approx(t[2] - mx);
+      return (lg2_approx(ss) + mx) * kLn2;
+    } else {
+      float q[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float xs = scaled ? M::mul(x[e], s[e]) : x[e];
+        if (c.ok(e)) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float dd = M::sub(xs, mu[k][e]);
+            q[k] = M::add(q[k], M::mul(dd, dd));
+          }
+        }
+      }
+      float t[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float qq = group_sum(q[k], c);
+        float v = M::add(M::mul(-0.5f, qq), c1[k]);
+        if (scaled) v = M::add(v, J);
+        t[k] = M::add(v, lw[k]);
+      }
+      float mx = fmaxf(fmaxf(t[0], t[1]), t[2]);
+      if (isinf(mx)) mx = 0.0f;
+      const float ss = M::add(M::add(M::exp(M::sub(t[0], mx)), M::exp(M::sub(t[1], mx))), M::exp(M::sub(t[2], mx)));
+      return M::add(M::log(ss), mx);
     }
-    float mx = fmaxf(fmaxf(t[0], t[1]), t[2]);
-    if (isinf(mx)) mx = 0.0f;
-    const float ss = M::add(M::add(M::exp(M::sub(t[0], mx)), M::exp(M::sub(t[1], mx))), M::exp(M::sub(t[2], mx)));
-    return M::add(M::log(ss), mx);
   }
 };
 

@@ -420,6 +420,86 @@ def test_pt_native_rng_statistics_vs_oracle():
     np.testing.assert_allclose(mh_g, mh_o, atol=0.02)
 
 
+def test_config4_tuned_kernel_laplace_increments_and_statistics():
+    """BASELINE config 4 on its tuned kernel (ThreeMixture d=50, 7 coordinates x 8 lanes, Laplace / UniformRadius, fast
+    math, native Philox).  (i) On a flattened target every proposal is accepted, so the stored differences ARE the
+    increments: Laplace(0, b_k) per coordinate with 2 b_k^2 = var / beta_k -- mean 0, E|z| = 1, E z^2 = 2, E z^4 = 24
+    in units of b_k, no correlation between coordinates or consecutive steps, at every temperature.  (ii) On the real
+    target (centres +-15): per-temperature Metropolis acceptance, swap acceptance and cold-chain ESJD against the
+    oracle composition with NumPy randomness (3 standard errors; ESJD 2 %)."""
+    dev = _cuda()
+    _, PT = _algs()
+    from rwm_pt_pytorch_b200.proposal_distributions import LaplaceProposal, UniformRadiusProposal
+    import rwm_pt_pytorch_b200.target_distributions as td
+    d, K = 50, 8
+    betas = O.geometric_ladder()
+    var = 2.38 ** 2 / d
+    centres = [[-15.0] + [0.0] * (d - 1), [0.0] * d, [15.0] + [0.0] * (d - 1)]
+    # (i) flat target: one mode at the origin seen through scaling factors of 1e-6
+    flat = td.ThreeMixtureDistributionTorch(d, scaling=True, device="cpu", mode_centers=[[0.0] * d] * 3)
+    flat.scaling_factors = torch.full((d,), 1e-6)
+    flat.log_jacobian = torch.sum(torch.log(flat.scaling_factors))
+    L, T = 8, 4096
+    lap = LaplaceProposal(d, torch.full((d,), var), 1.0, torch.device("cpu"), torch.float32)
+    algo = PT(d, None, flat, beta_ladder=betas, swap_every=10 ** 9, burn_in=0, device=dev, num_ladders=L, seed=11, store="all",
+              proposal_distribution=lap, initial_states=np.zeros((L, K, d), np.float32))
+    assert algo._require_batch().geometry() == (7, 8)
+    algo.generate_samples(T)
+    assert algo.mh_acceptance_rates.min().item() > 1 - 1e-3
+    x = torch.stack(algo.get_all_chains_gpu(), dim=1).double().cpu().numpy()      # per temperature (L, T+1, d) -> (L, K, T+1, d)
+    assert x.shape == (L, K, T + 1, d)
+    for k in range(K):
+        z = np.diff(x[:, k], axis=1).reshape(-1, d) / np.sqrt(np.float32(var) / np.float32(betas[k]) / 2.0)   # units of b_k
+        n = z.size
+        assert abs(z.mean()) < 5 * np.sqrt(2.0 / n), (k, z.mean())
+        assert abs(np.abs(z).mean() - 1.0) < 5 * np.sqrt(1.0 / n) + 2e-4, (k, np.abs(z).mean())
+        assert abs((z ** 2).mean() - 2.0) < 5 * np.sqrt(20.0 / n) + 1e-3, (k, (z ** 2).mean())
+        assert abs((z ** 4).mean() - 24.0) < 5 * np.sqrt((40320.0 - 576.0) / n) + 0.05, (k, (z ** 4).mean())
+        m = z.shape[0]
+        assert np.abs(z.mean(0)).max() < 5.5 * np.sqrt(2.0 / m)
+        corr = np.corrcoef(z.T)
+        assert np.abs(corr - np.eye(d)).max() < 5.5 / np.sqrt(m)
+        corr2 = np.corrcoef(np.abs(z).T)
+        assert np.abs(corr2 - np.eye(d)).max() < 5.5 / np.sqrt(m)
+        zz = np.diff(x[:, k], axis=1) / np.sqrt(np.float32(var) / np.float32(betas[k]) / 2.0)                  # (L, T, d)
+        lag = np.concatenate([zz[:, :-1].reshape(-1, d), zz[:, 1:].reshape(-1, d)], axis=1)                    # step t vs t+1
+        cl = np.corrcoef(lag.T)[:d, d:]
+        assert np.abs(cl).max() < 5.5 / np.sqrt(lag.shape[0])
+    # (ii) real target statistics vs the oracle composition
+    L_o, T2, burn, se = 24, 1500, 300, 10
+    rs = np.random.RandomState(21)
+    var_vec = np.full(d, var, np.float32)
+    t = td.ThreeMixtureDistributionTorch(d, device="cpu", mode_centers=centres)
+    spec = t.spec()
+    for kind in ("laplace", "uniform"):
+        if kind == "laplace":
+            raw = rs.rand(T2, L_o, K, d).astype(np.float32)
+            inc = np.stack([O.laplace_increments(raw[:, :, k].reshape(-1, d), var_vec, betas[k]).reshape(T2, L_o, d) for k in range(K)], axis=2)
+            prop = LaplaceProposal(d, torch.tensor(var_vec), 1.0, torch.device("cpu"), torch.float32)
+        else:
+            rz, rr = rs.randn(T2, L_o, K, d).astype(np.float32), rs.rand(T2, L_o, K).astype(np.float32)
+            inc = np.stack([O.uniform_radius_increments(rz[:, :, k].reshape(-1, d), rr[:, :, k].reshape(-1), 1.0, betas[k]).reshape(T2, L_o, d) for k in range(K)], axis=2)
+            prop = UniformRadiusProposal(d, 1.0, 1.0, torch.device("cpu"), torch.float32)
+        R = sum(1 for s_ in range(1, T2 + 1) if s_ % se == 0 and s_ > burn)
+        ora = O.pt_run(spec, np.zeros((L_o, K, d), np.float32), betas, inc, rs.rand(T2, L_o, K), rs.rand(R, L_o, K - 1), se,
+                       burn_in=burn, keep_states=False)
+        Lg = 1024
+        algo = PT(d, None, t, beta_ladder=betas, swap_every=se, burn_in=burn, device=dev, num_ladders=Lg, seed=5,
+                  proposal_distribution=prop, initial_states=np.zeros((Lg, K, d), np.float32))
+        assert algo._require_batch().geometry() == (7, 8)
+        algo.generate_samples(T2 - burn)
+        mh_g = algo.mh_acceptance_rates.cpu().numpy()              # (Lg, K)
+        mh_o = ora["mh_accepts"] / (T2 - burn)                     # (L_o, K)
+        err = np.hypot(mh_g.std(0, ddof=1) / np.sqrt(Lg), mh_o.std(0, ddof=1) / np.sqrt(L_o))
+        assert (np.abs(mh_g.mean(0) - mh_o.mean(0)) <= 3.5 * err + 1e-3).all(), (kind, mh_g.mean(0), mh_o.mean(0), err)
+        rate_g, rate_o = algo.swap_acceptance_rates, ora["swap_accepts"] / ora["swap_attempts"]
+        serr = np.hypot(rate_g.std(ddof=1) / np.sqrt(Lg), rate_o.std(ddof=1) / np.sqrt(L_o))
+        assert abs(rate_g.mean() - rate_o.mean()) <= 3 * serr, (kind, rate_g.mean(), rate_o.mean(), serr)
+        e_g, e_o = algo.esjd_per_ladder().cpu().numpy(), ora["cold_esjd"]
+        e_err = np.hypot(e_g.std(ddof=1) / np.sqrt(Lg), e_o.std(ddof=1) / np.sqrt(L_o))
+        assert abs(e_g.mean() - e_o.mean()) <= 3 * e_err + 0.02 * e_o.mean(), (kind, e_g.mean(), e_o.mean(), e_err)
+
+
 # ---- proposal plugins, swap kernel, ESJD kernel -----------------------------------------------------------
 def test_proposal_plugin_samplers_moments():
     dev = _cuda()
