@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Benchmark of the RWM / PT-RWM sampling hot path (contract: see the task statement; metric: BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c5|c5f]
 
 One "step" = one pass of the hot path over one batch: a single launch of the persistent fused kernel that advances
 every chain of the workload by `T` Metropolis steps (plus swap sweeps).  Default workload = BASELINE config 3, the
@@ -45,6 +45,16 @@ WORKLOADS = {
     "c5": dict(desc="C5 RWM FullRosenbrock d=100, 64 variances x 256 chains (16384 chains/GPU), accumulators only",
                kind="rwm", target="full_rosenbrock", dim=100, K=1, units=16384, T=20_000, burn_in=1000, swap_every=1,
                var=None, F=1895, S=201, bytes=0),
+    "c5f": dict(desc="C5 RWM NealFunnel d=100, 64 variances x 256 chains (16384 chains/GPU), accumulators only",
+                kind="rwm", target="neal_funnel", dim=100, K=1, units=16384, T=20_000, burn_in=1000, swap_every=1,
+                var=None, F=1315, S=202, bytes=0),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum of the hot kernel for one launch of the workload at its default run length,
+# from the committed `ncu --set full` captures (profiles/): (bytes, summary file)
+NCU_TRAFFIC = {
+    "c3": (1_189_120 + 38_144, "profiles/r1g_c3_mcmc_kernel_ncu_full_summary.txt"),
+    "c4": (2_869_760 + 1_613_624_000, "profiles/r1h_c4_mcmc_kernel_7x8_ncu_full_summary.txt"),
+    "c5": (7_150_592 + 0, "profiles/r1g_c5_mcmc_kernel_ncu_full_summary.txt"),
 }
 NOMINAL_SFU_GOPS = 148 * 16 * 1.965     # 16 SFU lanes / SM / clk
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e-3
@@ -58,6 +68,8 @@ def make_target(name, dim):
         return td.EvenRosenbrockTorch(dim, device="cpu")
     if name == "full_rosenbrock":
         return td.FullRosenbrockTorch(dim, device="cpu")
+    if name == "neal_funnel":
+        return td.NealFunnelTorch(dim, device="cpu")
     if name == "three_mixture":
         return td.ThreeMixtureDistributionTorch(dim, device="cpu", mode_centers=[[-15.0] + [0.0] * (dim - 1), [0.0] * dim,
                                                                                 [15.0] + [0.0] * (dim - 1)])
@@ -74,8 +86,10 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"]
+            if self.index is not None:
+                cmd += ["-i", str(self.index)]
+            self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -302,12 +316,14 @@ def main():
         for _ in range(args.warmup):
             batch.run(T)
             if world > 1:                                                 # also warms the NCCL communicator up
-                D.allreduce_statistics(D.local_statistics(algo), device=dev)
+                D.allreduce_statistics_tensor(D.local_statistics_tensor(algo))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local) if with_clocks else None
+        # one nvidia-smi poller per job (rank 0; it lists every GPU when the job has several): NVML queries take a driver
+        # lock that CUDA calls of the same process tree can wait on
+        sampler = ClockSampler(local if world == 1 else None) if (with_clocks and rank == 0) else None
         if sampler:
             sampler.start()
         evs = []
@@ -319,7 +335,7 @@ def main():
             batch.run(T)                                                  # ONE launch of the fused kernel
             launches += 1
             if world > 1:                                                 # the path's only collective: accumulators
-                reduced = D.allreduce_statistics(D.local_statistics(algo), device=dev)
+                reduced = D.allreduce_statistics_tensor(D.local_statistics_tensor(algo))   # device ops + NCCL, no host sync
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
@@ -327,7 +343,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        ms = sum(step_ms)
+        if reduced is not None:
+            reduced = D.statistics_from_tensor(reduced)
         if world > 1:
             tt = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -336,7 +355,7 @@ def main():
         rate = world * nc * T / (ms_per_step * 1e-3)
         algo._refresh_stats()
         return dict(rate=rate, ms_per_step=ms_per_step, launches=launches, clocks=clocks, algo=algo, batch=batch, t=t,
-                    reduced=reduced)
+                    reduced=reduced, step_ms=[round(x, 3) for x in step_ms])
 
     m = measure(wl, store, True)
     algo, batch = m["algo"], m["batch"]
@@ -379,7 +398,12 @@ def main():
         roof = {"bound": "fp32", "achieved": per_gpu * wl["F"] / 1e12, "peak": fp32_tf.value, "unit": "TFLOP/s",
                 "peak_source": "measured on this GPU (rwmpt_probe_peaks, dependent-free FFMA loop); nominal %.1f" % NOMINAL_FP32_TFLOPS}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None
+    default_shape = wl["T"] == WORKLOADS[args.workload]["T"] and wl["units"] == WORKLOADS[args.workload]["units"] and \
+        store == WORKLOADS[args.workload].get("store", "none")
+    tr = NCU_TRAFFIC.get(args.workload) if default_shape else None
+    roof["traffic"] = tr[0] if tr else None          # bytes per launch (ncu), next to the algorithmic bytes per launch
+    roof["traffic_source"] = tr[1] if tr else None
+    roof["algorithmic_bytes_per_launch"] = wl["bytes"] * wl["units"] * wl["K"] * wl["T"]
     roof["per_chain_step"] = {"F": wl["F"], "S": wl["S"], "stored_bytes": wl["bytes"]}
     roof["frac_sfu_measured"] = per_gpu * wl["S"] / (sfu_g.value * 1e9)
     roof["frac_sfu_nominal"] = per_gpu * wl["S"] / (NOMINAL_SFU_GOPS * 1e9)
@@ -395,7 +419,7 @@ def main():
         "config": {"workload": wl["desc"], "steps_per_launch": wl["T"], "chains_per_gpu": wl["units"] * wl["K"],
                    "lanes_per_chain": args.lanes or "auto", "l2": "256 MiB flush write between timed steps",
                    "rng": "in-kernel Philox4x32-10", "math": "fast"},
-        "gpu_launches": m["launches"], "clocks": m["clocks"], "roofline": roof,
+        "gpu_launches": m["launches"], "step_ms": m["step_ms"], "clocks": m["clocks"], "roofline": roof,
         "esjd": esjd, "esjd_per_sec": None if esjd is None else esjd * m["rate"] / wl["K"],
         "acceptance_rate": float(batch.accept_count.sum().item()) / max(post * batch.n_chains, 1),
     }

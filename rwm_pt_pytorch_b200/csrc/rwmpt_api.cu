@@ -658,7 +658,7 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
   e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   int rc = RWMPT_OK;
-  // one device arena for every staged buffer (a single cudaMalloc / cudaFree per call), 256-byte aligned slices
+  // one device arena for every staged buffer (a single stream-ordered allocation per call), 256-byte aligned slices
   struct Want { const void* host; size_t bytes; bool in, out; void** slot; };
   std::vector<Want> wants;
   auto stage = [&](const void* host, size_t bytes, bool in, bool out, void** slot) {
@@ -686,8 +686,20 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
   for (auto& w : wants) total += (w.bytes + 255) & ~(size_t)255;
   char* arena = nullptr;
   if (total) {
-    e = cudaMalloc((void**)&arena, total);
-    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc");
+    // stream-ordered allocation from the device's default pool, which keeps its memory between calls (release threshold
+    // raised once per device): after the first call this is a pool hit, not a cudaMalloc / cudaFree pair that
+    // serialises against every other process and context on the node
+    static bool pool_kept[64] = {};
+    if (device >= 0 && device < 64 && !pool_kept[device]) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_kept[device] = true;
+    }
+    e = cudaMallocAsync((void**)&arena, total, st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync");
   }
   size_t off = 0;
   for (auto& w : wants) {
@@ -712,9 +724,9 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
       d2h += b.bytes;
     }
   }
+  if (arena) cudaFreeAsync(arena, st);
   e = cudaStreamSynchronize(st);
   if (!rc && e != cudaSuccess) rc = cuda_fail(e, "stream synchronize");
-  if (arena) cudaFree(arena);
   cudaStreamDestroy(st);
   if (h2d_bytes) *h2d_bytes = h2d;
   if (d2h_bytes) *d2h_bytes = d2h;

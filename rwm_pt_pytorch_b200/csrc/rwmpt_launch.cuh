@@ -31,7 +31,8 @@ cudaError_t launch_mcmc_one(const KernelArgs& a_in, const LaunchGeom& g, cudaStr
     while ((c * wpc) % 4) ++c;                         // same number of warps on each of the SM's four schedulers
     const long long P = (long long)g.sms * c;
     const long long min_slice = forced ? 16 : 4096;
-    bool want = forced || (P > g.grid && c * wpc <= 16 && a_in.n_steps >= 8 * min_slice);
+    // measured on C3 (profiles/r1h_c3_schedule_vs_run_length.txt): the ticketed launch wins from ~1.5e5 steps per launch
+    bool want = forced || (P > g.grid && c * wpc <= 16 && a_in.n_steps >= 40 * min_slice);
     if (want && a_in.n_steps >= 2 * min_slice) {
       int nb = 0;
       cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, g.threads, g.smem);

@@ -47,6 +47,35 @@ def local_statistics(algo) -> Dict[str, float]:
     return out
 
 
+def local_statistics_tensor(algo) -> torch.Tensor:
+    """The same six accumulators as `local_statistics`, as one fp64 tensor on the sampler's device, computed with device
+    ops only (no host synchronisation): what a timed loop enqueues between the kernel and the all-reduce."""
+    b = algo._batch
+    dev = b.accept_count.device
+    post = b.post_burn_in_steps()
+    z = torch.zeros((), dtype=torch.float64, device=dev)
+    parts = [b.accept_count.sum().to(torch.float64), z + float(post * b.n_chains)]
+    if b.K == 1:
+        parts += [b.sq_jump_sum.sum(), z, z, z]
+    else:
+        acc = b.swap_accepts[:, : b.K - 1].to(torch.float64)
+        betas = b.beta.view(b.L, b.K)[0].to(torch.float64)
+        parts += [b.sq_jump_sum.view(b.L, b.K)[:, 0].sum(), z + float(b.swap_rounds() * (b.K - 1) * b.L), acc.sum(),
+                  (acc.sum(dim=0) * (betas[:-1] - betas[1:]) ** 2).sum()]
+    return torch.stack([p.to(torch.float64) for p in parts])
+
+
+def allreduce_statistics_tensor(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place SUM all-reduce of a `local_statistics_tensor` (asynchronous on the current stream with NCCL)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def statistics_from_tensor(t: torch.Tensor) -> Dict[str, float]:
+    return {k: float(v) for k, v in zip(STAT_KEYS, t.tolist())}
+
+
 def allreduce_statistics(stats: Dict[str, float], device=None, group=None) -> Dict[str, float]:
     """SUM all-reduce of the accumulators over all ranks (the path's only collective besides the sample gather)."""
     t = torch.tensor([float(stats.get(k, 0.0)) for k in STAT_KEYS], dtype=torch.float64, device=device)

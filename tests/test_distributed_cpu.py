@@ -78,3 +78,36 @@ def test_single_process_paths_are_identity():
     assert D.allreduce_statistics(st) == {k: float(st[k]) for k in D.STAT_KEYS}
     x = torch.zeros(3, 2, 2)
     assert D.gather_samples(x, [3]) is x
+
+
+class _FakeBatch:
+    """CPU stand-in for the sampler's batch (only the fields the statistics helpers read)."""
+
+    def __init__(self, L, K, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.L, self.K, self.n_chains = L, K, L * K
+        self.accept_count = torch.randint(0, 1000, (L * K,), generator=g, dtype=torch.int64)
+        self.sq_jump_sum = torch.rand(L * K, generator=g, dtype=torch.float64) * 50
+        self.swap_accepts = torch.randint(0, 40, (L, max(K - 1, 1)), generator=g, dtype=torch.int64)
+        self.beta = torch.tensor([0.5 ** k for k in range(K)], dtype=torch.float32).repeat(L)
+
+    def post_burn_in_steps(self):
+        return 400
+
+    def swap_rounds(self):
+        return 40
+
+
+class _FakeAlgo:
+    def __init__(self, L, K, seed):
+        self._batch = _FakeBatch(L, K, seed)
+
+
+@pytest.mark.parametrize("K", [1, 8])
+def test_device_side_statistics_match_the_host_side_ones(K):
+    """The sync-free tensor form used inside bench.py's timed loop carries the same six accumulators as the dict form."""
+    algo = _FakeAlgo(6, K, 3)
+    want = D.local_statistics(algo)
+    got = D.statistics_from_tensor(D.allreduce_statistics_tensor(D.local_statistics_tensor(algo)))
+    for k in D.STAT_KEYS:
+        assert got[k] == pytest.approx(want[k], rel=1e-12), k
