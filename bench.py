@@ -264,6 +264,36 @@ def e2e_run(wl, t, batch, dev_index, T, reps):
     return float(np.median(times)), int(h2d.value), int(d2h.value), accept, [round(x * 1e3, 2) for x in times]
 
 
+def aux_kernel_rates(dev, hbm_peak):
+    """The path's second hand-written kernel, the ESJD reduction over stored samples (HBM-read bound: 4*n*d algorithmic
+    bytes per chain), timed alone with CUDA events on a buffer several times larger than L2."""
+    import torch
+    from rwm_pt_pytorch_b200 import _lib
+    lib = _lib.load()
+    out = {}
+    for name, (B, S, d) in {"esjd_reduce d=50": (4096, 1025, 50), "esjd_reduce d=20": (8192, 2049, 20)}.items():
+        x = torch.randn((B, S, d), device=dev, dtype=torch.float32)
+        res = torch.empty(B, device=dev, dtype=torch.float64)
+        moved = torch.empty(B, device=dev, dtype=torch.int64)
+        row = {}
+        for form, mv in (("flat", None), ("with_moved_count", moved.data_ptr())):
+            times = []
+            for i in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.check(lib.rwmpt_esjd_reduce(x.data_ptr(), B, S, 0, S, d, res.data_ptr(), mv, _lib.stream_ptr(dev)))
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    times.append(e0.elapsed_time(e1))
+            gbs = x.numel() * 4 / (float(np.mean(times)) * 1e-3) / 1e9
+            row[form] = {"ms": float(np.mean(times)), "GB/s": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
+        row["bytes"] = x.numel() * 4
+        out[name] = row
+        del x
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -437,6 +467,8 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "chain-steps/s", "cores": 1, "kind": "port",
                                 "sample": f"NumPy oracle port, 1 process, {units} {'ladders' if wl['kind'] == 'pt' else 'chains'} x {Tc} steps "
                                           f"({wall:.1f} s wall); all-core figure: bench.py --impl reference"}
+    if world == 1 and args.workload == "c3" and not args.no_e2e:
+        line["aux_kernels"] = aux_kernel_rates(dev, hbm_peak)
     if args.also and world == 1:
         line["also"] = {}
         for name in args.also.split(","):

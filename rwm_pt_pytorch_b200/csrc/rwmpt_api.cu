@@ -344,7 +344,8 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(float* __restrict__ state,
   }
 }
 
-// ---- ESJD reduction over stored samples: warp per row-pair, block partials, one atomic per CTA ---
+// ---- ESJD reduction over stored samples with the per-chain count of rows that moved: warp per row-pair, block
+// partials, one atomic per CTA (the form without the count is esjd_flat_kernel below) ---
 __global__ void __launch_bounds__(256) esjd_kernel(const float* __restrict__ samples, long long stride, long long first,
                                                    long long n, int d, int ctas_per_chain, double* __restrict__ out,
                                                    unsigned long long* __restrict__ moved) {
@@ -374,6 +375,57 @@ __global__ void __launch_bounds__(256) esjd_kernel(const float* __restrict__ sam
     for (int w = 0; w < n_warps; ++w) { t += s_acc[w]; tm += s_mv[w]; }
     atomicAdd(&out[chain], t / (double)(n - 1));
     if (moved) atomicAdd(&moved[chain], tm);
+  }
+}
+
+// ---- ESJD reduction, bandwidth form (no per-row output wanted): the chain's retained rows are one flat array f[n*d] and
+// sum_m ||x_m - x_{m-1}||^2 = sum_{j >= d} (f[j] - f[j-d])^2, so every thread streams aligned VW-float vectors of f and of
+// f shifted by one row (the shifted stream re-reads lines the first stream fetched d floats earlier: L1 / L2 hits, HBM
+// sees each byte once), four vector pairs in flight per thread, no shuffle inside the loop.  Algorithmic bytes: 4 n d
+// per chain.  HBM-read bound.
+template <int VW> struct VecOf;
+template <> struct VecOf<4> { using T = float4; };
+template <> struct VecOf<2> { using T = float2; };
+template <> struct VecOf<1> { using T = float; };
+__device__ __forceinline__ float sqdiff(float4 a, float4 b) {
+  const float x = a.x - b.x, y = a.y - b.y, z = a.z - b.z, w = a.w - b.w;
+  return fmaf(x, x, fmaf(y, y, fmaf(z, z, w * w)));
+}
+__device__ __forceinline__ float sqdiff(float2 a, float2 b) {
+  const float x = a.x - b.x, y = a.y - b.y;
+  return fmaf(x, x, y * y);
+}
+__device__ __forceinline__ float sqdiff(float a, float b) { return (a - b) * (a - b); }
+
+template <int VW>
+__global__ void __launch_bounds__(256) esjd_flat_kernel(const float* __restrict__ samples, long long stride, long long first,
+                                                        long long n, int d, int ctas_per_chain, double* __restrict__ out) {
+  using V = typename VecOf<VW>::T;
+  const long long chain = blockIdx.x / ctas_per_chain;
+  const int part = blockIdx.x % ctas_per_chain;
+  const V* prev = reinterpret_cast<const V*>(samples + (chain * stride + first) * d);
+  const V* cur = reinterpret_cast<const V*>(samples + (chain * stride + first + 1) * d);
+  const long long total = (n - 1) * d / VW;                       // vectors of jumps (d % VW == 0)
+  const long long per = (total + ctas_per_chain - 1) / ctas_per_chain;
+  const long long lo = part * per;
+  const long long hi = lo + per < total ? lo + per : total;
+  double acc = 0.0;
+  long long v = lo + threadIdx.x;
+  for (; v + 3 * 256 < hi; v += 4 * 256) {
+    const V c0 = cur[v], c1 = cur[v + 256], c2 = cur[v + 512], c3 = cur[v + 768];
+    const V p0 = prev[v], p1 = prev[v + 256], p2 = prev[v + 512], p3 = prev[v + 768];
+    acc += (double)((sqdiff(c0, p0) + sqdiff(c1, p1)) + (sqdiff(c2, p2) + sqdiff(c3, p3)));
+  }
+  for (; v < hi; v += 256) acc += (double)sqdiff(cur[v], prev[v]);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  __shared__ double s_acc[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_acc[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_acc[w];
+    atomicAdd(&out[chain], t / (double)(n - 1));
   }
 }
 
@@ -526,6 +578,24 @@ int rwmpt_esjd_reduce(const float* samples, int64_t n_chains, int64_t stride, in
     if (e != cudaSuccess) return cuda_fail(e, "memset moved_out");
   }
   if (n < 2) return RWMPT_OK;  // fewer than two rows: ESJD is 0 (rwm_gpu_optimized.py:526-527)
+  if (!moved_out) {
+    // bandwidth form: 148 SMs x 8 resident CTAs, each with at least ~16 KiB of jumps to stream
+    const uintptr_t p = reinterpret_cast<uintptr_t>(samples);
+    const int vw = (dim % 4 == 0 && p % 16 == 0) ? 4 : ((dim % 2 == 0 && p % 8 == 0) ? 2 : 1);
+    const long long vecs = (n - 1) * dim / vw;
+    long long want = (148LL * 8 + n_chains - 1) / n_chains;
+    long long maxp = (vecs + 1023) / 1024;
+    long long cpc = want < 1 ? 1 : (want > maxp ? maxp : want);
+    if (cpc < 1) cpc = 1;
+    if (n_chains * cpc > 2147483647LL) return fail(RWMPT_ENOTSUP, "too many chains for esjd_reduce");
+    const unsigned grid = (unsigned)(n_chains * cpc);
+    if (vw == 4) esjd_flat_kernel<4><<<grid, 256, 0, st>>>(samples, stride, first, n, dim, (int)cpc, esjd_out);
+    else if (vw == 2) esjd_flat_kernel<2><<<grid, 256, 0, st>>>(samples, stride, first, n, dim, (int)cpc, esjd_out);
+    else esjd_flat_kernel<1><<<grid, 256, 0, st>>>(samples, stride, first, n, dim, (int)cpc, esjd_out);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "esjd kernel launch");
+    return RWMPT_OK;
+  }
   long long want = (148LL * 8 + n_chains - 1) / n_chains;  // enough CTAs to fill the machine
   long long maxp = (n - 1 + 7) / 8;
   int cpc = (int)(want < 1 ? 1 : (want > maxp ? maxp : want));

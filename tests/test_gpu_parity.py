@@ -582,6 +582,21 @@ def test_esjd_reduction_kernel():
             assert O.esjd_from_chain(x[0, :first + n], first) == pytest.approx(out[0].item(), rel=1e-5)
         else:
             assert (out == 0).all()
+        # without the moved-row count the bandwidth form runs (flat float4 / float2 / scalar streams)
+        out2 = torch.empty(B, device=dev, dtype=torch.float64)
+        _lib.check(lib.rwmpt_esjd_reduce(xd.data_ptr(), B, S, first, n, d, out2.data_ptr(), None, _lib.stream_ptr(dev)))
+        np.testing.assert_allclose(out2.cpu().numpy(), out.cpu().numpy(), rtol=1e-6, atol=0)
+    # a size that gives every CTA several unrolled iterations, and a misaligned base pointer (scalar stream)
+    B, S, d = 7, 5000, 20
+    x = np.cumsum(rs.randn(B, S, d), axis=1).astype(np.float32)
+    flat = torch.zeros(B * S * d + 1, device=dev, dtype=torch.float32)
+    for off in (0, 1):
+        view = flat[off:off + B * S * d]
+        view.copy_(torch.tensor(x.reshape(-1), device=dev))
+        out = torch.empty(B, device=dev, dtype=torch.float64)
+        _lib.check(lib.rwmpt_esjd_reduce(view.data_ptr(), B, S, 1, S - 1, d, out.data_ptr(), None, _lib.stream_ptr(dev)))
+        seg = x[:, 1:].astype(np.float64)
+        np.testing.assert_allclose(out.cpu().numpy(), ((seg[:, 1:] - seg[:, :-1]) ** 2).sum(-1).mean(axis=1), rtol=1e-6)
 
 
 # ---- edge cases, resumability, sharding invariance, host-buffer entry --------------------------------------
