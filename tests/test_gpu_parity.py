@@ -707,6 +707,84 @@ def test_balanced_schedule_is_bit_identical_to_plain(store):
     torch.testing.assert_close(out[0][2], out[1][2], rtol=1e-6, atol=0)
 
 
+def test_full_size_config3_properties():
+    """BASELINE config 3 at its full width (1024 ladders x 8 temperatures, RoughCarpet d=20, swap_every 10, burn-in 2000):
+    size-independent properties instead of an oracle run -- (a) one launch == two resumed launches, (b) two shards of 512
+    ladders with global chain ids == the single job (what each GPU of a 2-GPU job computes), (c) the balanced (ticketed)
+    schedule == the plain one, all bit for bit on states and integer accumulators; (d) the pooled swap acceptance matches
+    the reference's recorded 0.2795 (one ladder, 50 000 steps) within its Monte-Carlo error, and the
+    cold-chain ESJD per ladder is consistent across ladders (no ladder stuck)."""
+    dev = _cuda()
+    _, PT = _algs()
+    t = product_target("rough_carpet_d20")
+    L, T, burn = 1024, 12000, 2000
+    kw = dict(geom_temp_spacing=True, swap_every=10, burn_in=burn, device=dev, store="none", seed=1)
+
+    def run(n, base, parts, sched):
+        p = PT(20, 0.9, t, num_ladders=n, chain_id_base=base, **kw)
+        b = p._require_batch()
+        b.schedule = sched
+        for k in parts:
+            b.run(k)
+        p._refresh_stats()
+        return p
+
+    one = run(L, 0, [T], 1)
+    two = run(L, 0, [4999, T - 4999], 1)            # resume on an odd step, inside burn-in's tail
+    bal = run(L, 0, [T], 2)
+    s1, s2 = run(L // 2, 0, [T], 1), run(L // 2, (L // 2) * 8, [T], 1)
+    for other in (two, bal):
+        assert torch.equal(one.current_states, other.current_states)
+        assert torch.equal(one._batch.logp, other._batch.logp)
+        assert torch.equal(one._batch.accept_count, other._batch.accept_count)
+        assert torch.equal(one._batch.swap_accepts, other._batch.swap_accepts)
+        torch.testing.assert_close(one._batch.sq_jump_sum, other._batch.sq_jump_sum, rtol=1e-6, atol=0)
+    assert torch.equal(torch.cat([s1.current_states, s2.current_states]), one.current_states)
+    assert torch.equal(torch.cat([s1._batch.accept_count, s2._batch.accept_count]), one._batch.accept_count)
+    assert s1.num_swap_acceptances + s2.num_swap_acceptances == one.num_swap_acceptances
+    rates = one.swap_acceptance_rates
+    assert abs(rates.mean() - 0.2795) < 0.01, rates.mean()
+    e = one.esjd_per_ladder().cpu().numpy()
+    assert e.min() > 0 and abs(np.median(e) - e.mean()) < 0.25 * e.mean()
+
+
+def test_full_size_config4_stored_trajectories_properties():
+    """BASELINE config 4 at its full width (512 ladders, ThreeMixture d=50, Laplace, every step of all 8 chains stored):
+    the trajectory buffer must be self-consistent with the accumulators -- squared jumps recomputed from the stored rows ==
+    the kernel's running accumulator == the ESJD reduction kernel over the buffer -- and two shards, each resumed mid-run,
+    must reproduce the single job's stored samples bit for bit."""
+    dev = _cuda()
+    _, PT = _algs()
+    from rwm_pt_pytorch_b200.proposal_distributions import LaplaceProposal
+    import rwm_pt_pytorch_b200.target_distributions as td
+    d, K, L, T = 50, 8, 512, 400
+    centres = [[-15.0] + [0.0] * (d - 1), [0.0] * d, [15.0] + [0.0] * (d - 1)]
+    t = td.ThreeMixtureDistributionTorch(d, device="cpu", mode_centers=centres)
+
+    def make(n, base):
+        lap = LaplaceProposal(d, torch.full((d,), 2.38 ** 2 / d), 1.0, torch.device("cpu"), torch.float32)
+        return PT(d, None, t, geom_temp_spacing=True, swap_every=10, burn_in=0, device=dev, store="all", seed=3,
+                  num_ladders=n, chain_id_base=base, proposal_distribution=lap, pre_allocate_steps=T,
+                  initial_states=np.zeros((n, K, d), np.float32))
+
+    full = make(L, 0)
+    full.generate_samples(T)
+    b = full._batch
+    assert b.geometry() == (7, 8)
+    x = b.samples.view(L, K, b.capacity, d)[:, :, :T + 1]                 # row 0 = initial state
+    jumps = ((x[:, :, 1:].double() - x[:, :, :-1].double()) ** 2).sum(-1)   # (L, K, T)
+    torch.testing.assert_close(jumps.sum(-1).view(-1), b.sq_jump_sum, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(b.esjd_from_samples(0, T + 1), jumps.mean(-1).view(-1), rtol=1e-6, atol=1e-9)
+    assert torch.isfinite(x).all()
+    h1, h2 = make(L // 2, 0), make(L // 2, (L // 2) * K)
+    for h in (h1, h2):
+        hb = h._require_batch()
+        hb.allocate_storage("all", T + 1, 1) if hb.samples is None else None
+        hb.run(151); hb.run(T - 151); h._refresh_stats()
+    both = torch.cat([h1._batch.samples[:, :T + 1], h2._batch.samples[:, :T + 1]])
+    assert torch.equal(both, b.samples[:, :T + 1])
+
+
 def test_step_api_and_reference_bookkeeping():
     """step() one at a time equals one generate_samples launch; reference attribute semantics hold."""
     dev = _cuda()
