@@ -299,8 +299,8 @@ __device__ __forceinline__ bool swap_accept(float bj, float bk, float lj, float 
   return u < p;  // NaN -> false
 }
 
-// ---- flush of a chain's staged rows to HBM (called every `stage_rows` retained steps; kept out of line so that the
-// storing fast loop stays small).  `rs` = staged row stride in floats (the chain's E*W slots, padding included), `d` =
+// ---- flush of a chain's staged rows to HBM (called every `stage_rows` retained steps).
+// `rs` = staged row stride in floats (the chain's E*W slots, padding included), `d` =
 // row length in HBM.  rs == d: the staged block is the HBM block, one flat vector copy; otherwise row by row.  The W
 // lanes of the chain copy consecutive vectors, so every 32-byte sector is written whole, once.
 template <class V>
@@ -315,7 +315,7 @@ __device__ __forceinline__ void copy_vectors(const float* __restrict__ src, floa
   for (; v < nv; v += W) dv[v] = sv[v];
 }
 
-__device__ __noinline__ void stage_copy(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ lp_src,
+__device__ __forceinline__ void stage_copy(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ lp_src,
                                         float* __restrict__ lp_dst, int rows, int rs, int d, int vw, int sub, int W) {
   if (rs == d) {
     const int n = rows * d;
