@@ -229,17 +229,14 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   if (r->samples) {
     // staging region after the swap region: S rows per chain, S = 8 unless that needs more than ~64 KiB per CTA
     const size_t swap_floats = (g.smem / sizeof(float) + 3) & ~(size_t)3;
-    const size_t rs = (size_t)g.E * g.W;  // staged row stride: the chain's slots, padding included (== d when E*W == d)
     int S = 16;  // rows staged per chain: as many as keep the CTA's staging region under ~24 KiB (several CTAs per SM)
-    while (S > 1 && (size_t)g.chains_per_cta * (((size_t)S * rs + 3) & ~(size_t)3) * sizeof(float) > 24 * 1024) S >>= 1;
-    const size_t st_stride = ((size_t)S * rs + 3) & ~(size_t)3;
+    while (S > 1 && (size_t)g.chains_per_cta * (((size_t)S * d + 3) & ~(size_t)3) * sizeof(float) > 24 * 1024) S >>= 1;
+    const size_t st_stride = ((size_t)S * d + 3) & ~(size_t)3;
     const size_t lp_floats = ((size_t)g.chains_per_cta * S + 1) & ~(size_t)1;
     a.stage_rows = S;
     a.stage_off = (int)swap_floats;
     const uintptr_t p = reinterpret_cast<uintptr_t>(r->samples);
-    int vw = (d % 4 == 0 && p % 16 == 0) ? 4 : ((d % 2 == 0 && p % 8 == 0) ? 2 : 1);
-    while (vw > 1 && rs % vw) vw >>= 1;   // row-wise flush: every staged row must start on a vector boundary
-    a.stage_vw = vw;
+    a.stage_vw = (d % 4 == 0 && p % 16 == 0) ? 4 : ((d % 2 == 0 && p % 8 == 0) ? 2 : 1);
     g.smem = (swap_floats + (size_t)g.chains_per_cta * st_stride + lp_floats) * sizeof(float);
   }
   cudaError_t e = dispatch_mcmc(r->target.family, a, g, ieee, (cudaStream_t)stream);

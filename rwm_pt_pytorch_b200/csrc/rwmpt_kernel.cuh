@@ -299,42 +299,6 @@ __device__ __forceinline__ bool swap_accept(float bj, float bk, float lj, float 
   return u < p;  // NaN -> false
 }
 
-// ---- flush of a chain's staged rows to HBM (called every `stage_rows` retained steps).
-// `rs` = staged row stride in floats (the chain's E*W slots, padding included), `d` =
-// row length in HBM.  rs == d: the staged block is the HBM block, one flat vector copy; otherwise row by row.  The W
-// lanes of the chain copy consecutive vectors, so every 32-byte sector is written whole, once.
-template <class V>
-__device__ __forceinline__ void copy_vectors(const float* __restrict__ src, float* __restrict__ dst, int nv, int sub, int W) {
-  const V* sv = reinterpret_cast<const V*>(src);
-  V* dv = reinterpret_cast<V*>(dst);
-  int v = sub;
-  for (; v + 3 * W < nv; v += 4 * W) {
-    const V q0 = sv[v], q1 = sv[v + W], q2 = sv[v + 2 * W], q3 = sv[v + 3 * W];
-    dv[v] = q0; dv[v + W] = q1; dv[v + 2 * W] = q2; dv[v + 3 * W] = q3;
-  }
-  for (; v < nv; v += W) dv[v] = sv[v];
-}
-
-__device__ __forceinline__ void stage_copy(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ lp_src,
-                                        float* __restrict__ lp_dst, int rows, int rs, int d, int vw, int sub, int W) {
-  if (rs == d) {
-    const int n = rows * d;
-    if (vw == 4) copy_vectors<float4>(src, dst, n >> 2, sub, W);
-    else if (vw == 2) copy_vectors<float2>(src, dst, n >> 1, sub, W);
-    else copy_vectors<float>(src, dst, n, sub, W);
-  } else {
-    for (int r = 0; r < rows; ++r) {
-      const float* s_ = src + r * rs;
-      float* d_ = dst + (long long)r * d;
-      if (vw == 4) copy_vectors<float4>(s_, d_, d >> 2, sub, W);
-      else if (vw == 2) copy_vectors<float2>(s_, d_, d >> 1, sub, W);
-      else copy_vectors<float>(s_, d_, d, sub, W);
-    }
-  }
-  if (lp_dst != nullptr)
-    for (int r = sub; r < rows; r += W) lp_dst[r] = lp_src[r];
-}
-
 // One unit of work: the chains of CTA index `cta` (whole ladders) advanced by `n_steps` steps from global step
 // `step_offset`.  SLICED: the unit is one time slice of a balanced launch -- another CTA (possibly on another SM) ran
 // the previous slice, so state is read past L1 and the accumulators are updated with atomics.
@@ -412,43 +376,49 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
     store_m = (nxt - a.store_start) / a.thin - 1;
   }
   const long long store_chain = a.store_mode == RWMPT_STORE_ALL ? chain : ladder;
-  // Retained samples are staged in shared memory, S = a.stage_rows rows per chain; a staged row holds the chain's E*W
-  // slots (padding included, so the lanes store without masks) and the block is flushed by stage_copy with vector stores
-  // of a.stage_vw floats (layout in HBM (chain, row, dim): the S rows of one chain are adjacent).
+  // Retained samples are staged in shared memory, S = a.stage_rows rows per chain, and flushed as contiguous
+  // S*d-float blocks (layout (chain, row, dim): the S rows of one chain are adjacent in HBM) with vector stores of
+  // a.stage_vw floats (float4 when d % 4 == 0, float2 when d is even): one warp instruction writes 512 contiguous bytes.
   const int S = a.stage_rows;
-  const int RS = E * W;
-  const int st_stride = (S * RS + 3) & ~3;
+  const int st_stride = (S * d + 3) & ~3;
   float* st_base = smem + a.stage_off;                                  // [chains_per_cta][st_stride]
   float* st_lp_base = st_base + (size_t)a.chains_per_cta * st_stride;    // [chains_per_cta][S]
   float* st_x = st_base + (in_cta ? cl : 0) * st_stride;
-  float* st_lp = st_lp_base + (size_t)(in_cta ? cl : 0) * S;
-  float* st_row = st_x + c.base;                                        // this lane's slots of the next staged row
   const bool stage_me = storing && valid;
   const bool store_each = a.samples != nullptr && a.thin == 1 && s_first > a.store_start;  // every step of this run is retained
   int nbuf = 0;
   long long m_base = store_m;   // row index of staged row 0
   auto stage_flush = [&]() {
-    // no CTA barrier: a staging region is only touched by its own chain's lanes, which sit in one warp
+    // Each chain's W lanes copy their own chain's staged block: consecutive lanes write consecutive vectors, so every
+    // 32-byte sector is written whole exactly once; no CTA barrier (a staging region is only touched by its own warp).
     __syncwarp();
     long long rows = a.sample_rows - m_base;
     if (rows > nbuf) rows = nbuf;
     if (rows > 0 && stage_me) {
-      const long long row0 = store_chain * a.sample_stride + m_base;
-      stage_copy(st_x, a.samples + row0 * d, st_lp, a.sample_logp != nullptr ? a.sample_logp + row0 : nullptr, (int)rows, RS, d,
-                 a.stage_vw, c.sub, W);
+      const int n = (int)rows * d;
+      const float* src = st_x;
+      float* dst = a.samples + (store_chain * a.sample_stride + m_base) * d;
+      if (a.stage_vw == 4) {
+        for (int v = c.sub; v < (n >> 2); v += W) reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(src)[v];
+      } else if (a.stage_vw == 2) {
+        for (int v = c.sub; v < (n >> 1); v += W) reinterpret_cast<float2*>(dst)[v] = reinterpret_cast<const float2*>(src)[v];
+      } else {
+        for (int v = c.sub; v < n; v += W) dst[v] = src[v];
+      }
+      if (a.sample_logp != nullptr)
+        for (int r = c.sub; r < (int)rows; r += W) a.sample_logp[store_chain * a.sample_stride + m_base + r] = st_lp_base[(size_t)cl * S + r];
     }
     __syncwarp();
     m_base += nbuf;
     nbuf = 0;
-    st_row = st_x + c.base;
   };
   auto stage_row = [&](const float (&xs)[E], float lpv) {
     if (stage_me) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) st_row[e] = xs[e];
-      if (c.sub == 0) st_lp[nbuf] = lpv;
+      for (int e = 0; e < E; ++e)
+        if (c.ok(e)) st_x[nbuf * d + c.base + e] = xs[e];
+      if (c.sub == 0) st_lp_base[(size_t)cl * S + nbuf] = lpv;
     }
-    st_row += RS;
     ++nbuf;
     if (nbuf == S) stage_flush();
   };
