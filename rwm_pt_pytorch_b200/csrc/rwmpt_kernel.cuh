@@ -302,7 +302,7 @@ __device__ __forceinline__ bool swap_accept(float bj, float bk, float lj, float 
 // One unit of work: the chains of CTA index `cta` (whole ladders) advanced by `n_steps` steps from global step
 // `step_offset`.  SLICED: the unit is one time slice of a balanced launch -- another CTA (possibly on another SM) ran
 // the previous slice, so state is read past L1 and the accumulators are updated with atomics.
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool SLICED>
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool SLICED, bool STORE>
 __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long cta, const long long step_offset,
                                           const long long n_steps, const long long rounds_before) {
   using M = Mth<IEEE>;
@@ -368,8 +368,11 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
     swap_cd = nxt - s_first;
   }
   long long store_cd = -1, store_m = 0;
-  const bool storing = a.samples != nullptr && (a.store_mode == RWMPT_STORE_ALL || (a.store_mode == RWMPT_STORE_COLD && temp == 0));
-  if (a.samples != nullptr) {
+  // STORE = false: instantiation for runs without retained samples (a.samples == nullptr guaranteed by the launcher): no
+  // staging code at all, so the accumulators-only kernels do not depend on the store path
+  const bool has_samples = STORE && a.samples != nullptr;
+  const bool storing = has_samples && (a.store_mode == RWMPT_STORE_ALL || (a.store_mode == RWMPT_STORE_COLD && temp == 0));
+  if (has_samples) {
     const long long r = s_first - a.store_start;
     long long nxt = r <= 0 ? a.store_start + a.thin : s_first + ((a.thin - r % a.thin) % a.thin);
     store_cd = nxt - s_first;
@@ -385,7 +388,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   float* st_lp_base = st_base + (size_t)a.chains_per_cta * st_stride;    // [chains_per_cta][S]
   float* st_x = st_base + (in_cta ? cl : 0) * st_stride;
   const bool stage_me = storing && valid;
-  const bool store_each = a.samples != nullptr && a.thin == 1 && s_first > a.store_start;  // every step of this run is retained
+  const bool store_each = has_samples && a.thin == 1 && s_first > a.store_start;  // every step of this run is retained
   int nbuf = 0;
   long long m_base = store_m;   // row index of staged row 0
   auto stage_flush = [&]() {
@@ -576,7 +579,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
     n_acc += n_acc32; n_acc32 = 0;
 
     // 8. retained samples: layout (chain, row, dim)
-    if (a.samples != nullptr) {
+    if (has_samples) {
       if (store_each) {
         stage_row(x, lp);
       } else {
@@ -683,7 +686,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
       long long ev = n_steps - 1;                              // last step (also covers an odd tail)
       if (t < burn_t && burn_t - 1 < ev) ev = burn_t - 1;      // burn-in boundary inside a pair
       if (K > 1 && !sweep_fast && t + swap_cd < ev) ev = t + swap_cd;  // sweep due after that step
-      if (a.samples != nullptr && !store_each && t + store_cd < ev) ev = t + store_cd;
+      if (has_samples && !store_each && t + store_cd < ev) ev = t + store_cd;
       const bool post = t >= burn_t;
       const long long n_fast = h0 ? 0 : (ev - t) >> 1;         // whole pairs strictly before the event
       long long n_done = 0;                                    // pairs the fast loop ran (at most 2^30 per entry)
@@ -773,11 +776,15 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
         if (sweep_fast) swap_cd = sw_tracked ? 2ll * sw - 1 : swap_cd - 2ll * n_here;
       };
       // the retained-sample variant is a separate instantiation so that the accumulators-only loop stays lean
-      if (store_each) fast_pairs(std::true_type{});
-      else fast_pairs(std::false_type{});
+      if constexpr (STORE) {
+        if (store_each) fast_pairs(std::true_type{});
+        else fast_pairs(std::false_type{});
+      } else {
+        fast_pairs(std::false_type{});
+      }
       t += 2 * n_done;
       if (K > 1 && !sweep_fast) swap_cd -= 2 * n_done;
-      if (a.samples != nullptr) store_cd -= 2 * n_done;
+      if (has_samples) store_cd -= 2 * n_done;
       if (n_done < n_fast) continue;                           // more than 2^30 pairs: re-enter the fast loop
       // the pair that holds the event, through the general path (one copy of do_step: the two halves share the code)
       {
@@ -804,7 +811,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   }
 
   // epilogue: staged samples, state, log-density, accumulators
-  if (a.samples != nullptr && nbuf > 0) stage_flush();
+  if (has_samples && nbuf > 0) stage_flush();
   jump_d += (double)jump_f;
   n_acc += n_acc32;
   jump_d = group_sum_f64_w<WT>(jump_d, W);
@@ -841,10 +848,10 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
 // publish.  A ladder is always being advanced by exactly one CTA, the spare CTAs sleep, and the time a warp spends
 // alone on its scheduler (where it runs ~1.7x faster) is shared by all ladders instead of ending in an idle tail.
 // Results do not depend on the schedule: a slice resumes exactly like a host-level resume (step_offset).
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE>
 __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a) {
   if constexpr (TEST) {
-    mcmc_unit<Target, E, IEEE, WT, PF, EXACT, TEST, false>(a, (long long)blockIdx.x, a.step_offset, a.n_steps, a.rounds_before);
+    mcmc_unit<Target, E, IEEE, WT, PF, EXACT, TEST, false, STORE>(a, (long long)blockIdx.x, a.step_offset, a.n_steps, a.rounds_before);
   } else {
     // one call site for both schedules (the unit is large and force-inlined): a plain launch is a single "ticket"
     __shared__ unsigned s_ticket;
@@ -873,7 +880,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
         rb = (a.K > 1 && so > a.burn_in) ? so / a.swap_every - a.burn_in / a.swap_every : 0;
       }
       // (L1-bypassing loads and atomic accumulators of the sliced unit are harmless in a plain launch)
-      mcmc_unit<Target, E, IEEE, WT, PF, EXACT, TEST, true>(a, unit, so, n, rb);
+      mcmc_unit<Target, E, IEEE, WT, PF, EXACT, TEST, true, STORE>(a, unit, so, n, rb);
       if (!sliced) break;
       __threadfence();
       __syncthreads();

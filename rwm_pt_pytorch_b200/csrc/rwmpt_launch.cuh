@@ -15,9 +15,39 @@ namespace rwmpt {
 #define RWMPT_IEEE_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
 #endif
 
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE>
+cudaError_t launch_mcmc_store(const KernelArgs& a_in, const LaunchGeom& g, cudaStream_t st);
+
+// Fast (non-test) kernels exist twice: with and without the retained-sample path, so that the accumulators-only kernels
+// do not depend on the store code.  Measured on one box (profiles/r1i_store_split_ab.txt): C2 (EvenRosenbrock) gains 15 %
+// from its store-free instantiation, C5 / C4 are unchanged, and ptxas schedules RoughCarpet's store-free instantiation 5 %
+// worse than the combined kernel -- that family keeps the single combined kernel (SplitStore<...>::value = false).
+template <template <int, bool> class Target>
+struct SplitStore {
+  static constexpr bool value = true;
+};
+template <>
+struct SplitStore<RoughCarpet> {
+  static constexpr bool value = false;
+};
+template <>
+struct SplitStore<RoughCarpetPlain> {
+  static constexpr bool value = false;
+};
+
 template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
 cudaError_t launch_mcmc_one(const KernelArgs& a_in, const LaunchGeom& g, cudaStream_t st) {
-  auto kern = mcmc_kernel<Target, E, IEEE, WT, PF, EXACT, TEST>;
+  if constexpr (TEST || !SplitStore<Target>::value) {
+    return launch_mcmc_store<Target, E, IEEE, WT, PF, EXACT, TEST, true>(a_in, g, st);
+  } else {
+    if (a_in.samples != nullptr) return launch_mcmc_store<Target, E, IEEE, WT, PF, EXACT, TEST, true>(a_in, g, st);
+    return launch_mcmc_store<Target, E, IEEE, WT, PF, EXACT, TEST, false>(a_in, g, st);
+  }
+}
+
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE>
+cudaError_t launch_mcmc_store(const KernelArgs& a_in, const LaunchGeom& g, cudaStream_t st) {
+  auto kern = mcmc_kernel<Target, E, IEEE, WT, PF, EXACT, TEST, STORE>;
   if (g.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
