@@ -52,8 +52,8 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of the hot kernel for one launch of the workload at its default run length,
 # from the committed `ncu --set full` captures (profiles/): (bytes, summary file)
 NCU_TRAFFIC = {
-    "c3": (1_189_120 + 38_144, "profiles/r1g_c3_mcmc_kernel_ncu_full_summary.txt"),
-    "c4": (2_869_760 + 1_613_624_000, "profiles/r1h_c4_mcmc_kernel_7x8_ncu_full_summary.txt"),
+    "c3": (1_166_592 + 42_752, "profiles/r1j_c3_mcmc_kernel_ncu_full_summary.txt"),
+    "c4": (3_691_008 + 1_618_394_000, "profiles/r1j_c4_mcmc_kernel_ncu_full_summary.txt"),
     "c5": (7_150_592 + 0, "profiles/r1g_c5_mcmc_kernel_ncu_full_summary.txt"),
 }
 NOMINAL_SFU_GOPS = 148 * 16 * 1.965     # 16 SFU lanes / SM / clk

@@ -12,4 +12,7 @@ python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/plain2_$TAG.
 python bench.py --workload c2 --steps 1 --warmup 3 --no-cpu --no-e2e --T 200000 > gpurun_out/plain3_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:mcmc_kernel -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_c2 python bench.py --workload c2 --steps 1 --warmup 3 --no-cpu --no-e2e --T 200000 > gpurun_out/ncu_full2_$TAG.log 2>&1
 python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/plain4_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:mcmc_kernel -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_c4 python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full4_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:esjd_flat -s 4 -c 1 -f -o gpurun_out/prof_${TAG}_esjd python bench.py --steps 1 --warmup 3 --no-cpu --T 20000 > gpurun_out/ncu_esjd_$TAG.log 2>&1
-ls -la gpurun_out | grep $TAG
+# the merge back is capped at 64 MiB: summarise on the box, keep only the C3 report itself
+for w in c3 c2 c4 esjd; do [ -f gpurun_out/prof_${TAG}_$w.ncu-rep ] && python scripts/ncu_summary.py gpurun_out/prof_${TAG}_$w.ncu-rep > gpurun_out/summary_${TAG}_$w.txt 2>&1; done
+rm -f gpurun_out/prof_${TAG}_c2.ncu-rep gpurun_out/prof_${TAG}_c4.ncu-rep
+ls -la gpurun_out | grep $TAG; du -sh gpurun_out
