@@ -291,6 +291,33 @@ def aux_kernel_rates(dev, hbm_peak):
         row["bytes"] = x.numel() * 4
         out[name] = row
         del x
+    # the stand-alone plugin kernels behind target.log_density(x) and proposal.sample(n) (the iterative
+    # ladder construction evaluates up to 1e6 densities per estimate)
+    import rwm_pt_pytorch_b200.target_distributions as td
+    n, d = 4_000_000, 20
+    t = td.RoughCarpetDistributionTorch(d, device="cpu")
+    params = t.device_params(dev)
+    tgt = _lib.target_struct(t.family_id, d, params)
+    x = torch.randn((n, d), device=dev, dtype=torch.float32) * 4
+    res = torch.empty(n, device=dev, dtype=torch.float32)
+
+    def timed(fn):
+        times = []
+        for i in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                times.append(e0.elapsed_time(e1))
+        return float(np.mean(times))
+
+    ms = timed(lambda: _lib.check(lib.rwmpt_log_density(tgt, x.data_ptr(), n, res.data_ptr(), 0, _lib.stream_ptr(dev))))
+    out["log_density RoughCarpet d=20"] = {"ms": ms, "rows_per_s": n / (ms * 1e-3), "GB/s": n * (d + 1) * 4 / (ms * 1e-3) / 1e9,
+                                            "frac_of_hbm_peak": n * (d + 1) * 4 / (ms * 1e-3) / 1e9 / hbm_peak}
+    for fam, name in ((0, "normal"), (1, "laplace"), (2, "uniform_radius")):
+        ms = timed(lambda: _lib.check(lib.rwmpt_proposal_sample(fam, d, 0.5, None, n, 7, 0, x.data_ptr(), _lib.stream_ptr(dev))))
+        out[f"proposal_sample {name} d=20"] = {"ms": ms, "rows_per_s": n / (ms * 1e-3), "GB/s": n * d * 4 / (ms * 1e-3) / 1e9,
+                                                "frac_of_hbm_peak": n * d * 4 / (ms * 1e-3) / 1e9 / hbm_peak}
     return out
 
 

@@ -244,56 +244,72 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   return RWMPT_OK;
 }
 
-// ---- proposal sampler: one warp per row ---------------------------------------------------------
-__global__ void __launch_bounds__(128) proposal_kernel(int family, int d, float scale, const float* __restrict__ dscale,
-                                                       long long n, unsigned k0, unsigned k1, long long row_base,
+// ---- proposal sampler (plugin sample(n)): a group of G lanes per row, G = smallest power of two >= ceil(d / 4) (at most
+// a warp), each lane turning one Philox call into four coordinates and writing them as one float4 when the row layout
+// allows.  Counter = (block of four coordinates, tag, row id): counter-based, so the ball sampler's second pass
+// regenerates the normals instead of staging them.  Same fast transforms as the fused kernel.
+__global__ void __launch_bounds__(128) proposal_kernel(int family, int d, int G, float scale, const float* __restrict__ dscale,
+                                                       long long n, unsigned k0, unsigned k1, long long row_base, int vec4,
                                                        float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
+  const int sub = lane & (G - 1);
+  const int rows_per_warp = 32 / G;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int n_blk = (d + 3) / 4;
-  for (long long r = warp; r < n; r += n_warps) {
-    const unsigned long long rid = (unsigned long long)(row_base + r);
-    float n2 = 0.0f;
-    // pass 1 (UniformRadius only): squared norm of the normal vector; counter-based, so pass 2 regenerates it
+  const long long n_iter = (n + rows_per_warp - 1) / rows_per_warp;   // all lanes stay converged for the shuffles
+  for (long long it = warp; it < n_iter; it += n_warps) {
+    const long long r = it * rows_per_warp + lane / G;
+    const bool row_ok = r < n;
+    const unsigned long long rid = (unsigned long long)(row_base + (row_ok ? r : 0));
+    float f = scale;
     if (family == RWMPT_P_UNIFORM_RADIUS) {
-      for (int b = lane; b < n_blk; b += 32) {
+      // pass 1: squared norm of the row's normal vector (uniform.py:48-73: z / ||z|| * R * u^(1/d))
+      float n2 = 0.0f;
+      for (int b = sub; b < n_blk; b += G) {
         const uint4 w = philox4x32_10((unsigned)b, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
         float z[4];
-        box_muller<true>(w.x, w.y, z[0], z[1]);
-        box_muller<true>(w.z, w.w, z[2], z[3]);
+        box_muller<false>(w.x, w.y, z[0], z[1]);
+        box_muller<false>(w.z, w.w, z[2], z[3]);
+#pragma unroll
         for (int q = 0; q < 4; ++q)
           if (4 * b + q < d) n2 = fmaf(z[q], z[q], n2);
       }
-      for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFull, n2, o);
-    }
-    float f = scale;
-    if (family == RWMPT_P_UNIFORM_RADIUS) {
+      for (int o = G >> 1; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFull, n2, o);
       const uint4 w = philox4x32_10(0xffffffffu, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
-      const float nrm = sqrtf(n2);
+      const float nrm = sqrt_approx(n2);
       const float safe = nrm > 1e-12f ? nrm : 1.0f;
-      f = scale * powf(u01_from_bits(w.x), 1.0f / (float)d) / safe;
+      f = scale * ex2_approx(lg2_approx(u01_from_bits(w.x)) / (float)d) * rcp_approx(safe);
     }
-    for (int b = lane; b < n_blk; b += 32) {
+    for (int b = sub; b < n_blk; b += G) {
       const uint4 w = philox4x32_10((unsigned)b, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
       float v[4];
       if (family == RWMPT_P_LAPLACE) {
+        // laplace.py:47-69, as in pair_transform: 23 word bits -> r = 2u in [-1, 1); |increment| = -s ln(max(1 - |r|, 1e-6))
         const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float u = u01_from_bits(ww[q]) - 0.5f;
-          const float arg = fmaxf(-2.0f * fabsf(u), -0.999999f);
-          const float sg = (u > 0.0f) ? 1.0f : ((u < 0.0f) ? -1.0f : 0.0f);
           const int i = 4 * b + q;
           const float ds = (dscale && i < d) ? dscale[i] : 1.0f;
-          v[q] = -(scale * ds) * sg * log1pf(arg);
+          const float fbits = __uint_as_float((ww[q] & 0x007fffffu) | 0x3f800000u);
+          const float rr = fmaf(2.0f, fbits, -3.0f);
+          v[q] = copysignf(lg2_approx(fmaxf(1.0f - fabsf(rr), 1e-6f)) * (scale * ds * kLn2), rr);
         }
       } else {
-        box_muller<true>(w.x, w.y, v[0], v[1]);
-        box_muller<true>(w.z, w.w, v[2], v[3]);
+        box_muller<false>(w.x, w.y, v[0], v[1]);
+        box_muller<false>(w.z, w.w, v[2], v[3]);
+#pragma unroll
         for (int q = 0; q < 4; ++q) v[q] *= f;
       }
-      for (int q = 0; q < 4; ++q)
-        if (4 * b + q < d) out[r * d + 4 * b + q] = v[q];
+      if (row_ok) {
+        if (vec4) {
+          *reinterpret_cast<float4*>(out + r * d + 4 * b) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * b + q < d) out[r * d + 4 * b + q] = v[q];
+        }
+      }
     }
   }
 }
@@ -532,11 +548,16 @@ int rwmpt_proposal_sample(int32_t proposal_family, int32_t dim, float scale, con
   if (!(scale > 0.0f)) return fail(RWMPT_EINVAL, "scale must be positive");
   if (n == 0) return RWMPT_OK;
   if (!out) return fail(RWMPT_EINVAL, "out is NULL");
-  long long blocks = (n + 3) / 4;
+  const int n_blk = (dim + 3) / 4;
+  int G = 1;
+  while (G < n_blk && G < 32) G <<= 1;
+  const long long rows_per_cta = 4LL * (32 / G);
+  long long blocks = (n + rows_per_cta - 1) / rows_per_cta;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  proposal_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)cuda_stream>>>(proposal_family, dim, scale, dim_scale, n,
+  const int vec4 = (dim % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) ? 1 : 0;
+  proposal_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)cuda_stream>>>(proposal_family, dim, G, scale, dim_scale, n,
                                                                          (unsigned)(seed & 0xffffffffu), (unsigned)(seed >> 32),
-                                                                         row_id_base, out);
+                                                                         row_id_base, vec4, out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "proposal kernel launch");
   return RWMPT_OK;

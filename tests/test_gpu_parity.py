@@ -523,6 +523,19 @@ def test_proposal_plugin_samplers_moments():
     assert r.max().item() <= R * (1 + 1e-5)
     assert abs((r ** 2).mean().item() - R * R * d / (d + 2)) < 0.02 * R * R
     assert abs(s.mean().item()) < 0.01
+    # every lane-group width / store path of the sampler kernel: d = 20 (groups of 8, float4 stores), 50 (groups of 16,
+    # scalar stores), 3 (one lane per row), 200 (a whole warp per row, two blocks per lane), odd row counts
+    for d2, m in ((20, 100_001), (50, 50_003), (3, 300_000), (200, 20_001)):
+        for prop in (NormalProposal(d2, 0.5, 1.0, dev, torch.float32), LaplaceProposal(d2, torch.full((d2,), 0.5), 1.0, dev, torch.float32)):
+            s = prop.sample(m).double()
+            assert s.shape == (m, d2) and torch.isfinite(s).all()
+            np.testing.assert_allclose(s.var(dim=0).cpu().numpy(), np.full(d2, 0.5), rtol=0.06)
+            assert s.mean(dim=0).abs().max().item() < 6 * np.sqrt(0.5 / m)
+            cc = torch.corrcoef(s[:, :min(d2, 24)].T) - torch.eye(min(d2, 24), device=dev, dtype=torch.float64)
+            assert cc.abs().max().item() < 6 / np.sqrt(m)
+        s = UniformRadiusProposal(d2, 2.0, 1.0, dev, torch.float32).sample(m)
+        rr = s.norm(dim=1)
+        assert rr.max().item() <= 2.0 * (1 + 1e-5) and abs((rr ** 2).mean().item() - 4.0 * d2 / (d2 + 2)) < 0.03 * 4.0
 
 
 @pytest.mark.parametrize("swap_mode", ["reference", "exchange"])
