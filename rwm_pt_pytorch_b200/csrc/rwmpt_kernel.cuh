@@ -22,6 +22,9 @@
 #include "rwmpt_common.cuh"
 #include "rwmpt_targets.cuh"
 
+#ifndef RWMPT_CHUNK
+#define RWMPT_CHUNK 32  // pairs of steps between two flushes of the fp32 partial sums into the fp64 / 64-bit accumulators
+#endif
 #ifndef RWMPT_ORDER
 #define RWMPT_ORDER 0  // source order of the three streams inside the fast loop (ptxas keeps it as a tie-break)
 #endif
@@ -716,7 +719,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
         int sw = sw_tracked ? (int)((swap_cd + 1) >> 1) : 0x7fffffff;
         uint32_t plo = (uint32_t)pair, plo_end;  // low word of the pair being stepped / of the chunk's end
         auto chunk_len = [&]() -> int {
-          int m = left32 < 32 ? left32 : 32;
+          int m = left32 < RWMPT_CHUNK ? left32 : RWMPT_CHUNK;
           m = m < sw ? m : sw;
           const uint32_t room = 0u - (plo + 2u);   // draws before the low word of the Philox counter wraps (0: a full 2^32)
           if (room != 0u && (uint32_t)m > room) m = (int)room;
@@ -733,6 +736,16 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
           gen.gen(a.rk, plo + 2u, wn);
           plain_step(iA, uA, store_tag, xo, jadd, jf, cnt);
           plain_step(iB, uB, std::false_type{}, xo, jadd, jf, cnt);
+#elif RWMPT_ORDER == 2
+          pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, tA, tB, scale, dscale);
+          plain_step(iA, uA, store_tag, xo, jadd, jf, cnt);
+          gen.gen(a.rk, plo + 2u, wn);
+          plain_step(iB, uB, std::false_type{}, xo, jadd, jf, cnt);
+#elif RWMPT_ORDER == 3
+          plain_step(iA, uA, store_tag, xo, jadd, jf, cnt);
+          plain_step(iB, uB, std::false_type{}, xo, jadd, jf, cnt);
+          pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, tA, tB, scale, dscale);
+          gen.gen(a.rk, plo + 2u, wn);
 #else
           plain_step(iA, uA, store_tag, xo, jadd, jf, cnt);
           pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, tA, tB, scale, dscale);
