@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Benchmark of the RWM / PT-RWM sampling hot path (contract: see the task statement; metric: BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c5|c5f]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c4u|c5|c5f]
 
 One "step" = one pass of the hot path over one batch: a single launch of the persistent fused kernel that advances
 every chain of the workload by `T` Metropolis steps (plus swap sweeps).  Default workload = BASELINE config 3, the
@@ -42,6 +42,9 @@ WORKLOADS = {
     "c4": dict(desc="C4 PT-RWM ThreeMixture d=50 (+-15) K=8 Laplace var_i=2.38^2/50, 512 ladders/GPU, all chains stored",
                kind="pt", target="three_mixture", dim=50, K=8, units=512, T=2_000, burn_in=0, swap_every=10,
                var=2.38 ** 2 / 50, F=1066, S=55, bytes=204, proposal="laplace", store="all"),
+    "c4u": dict(desc="C4 PT-RWM ThreeMixture d=50 (+-15) K=8 UniformRadius r=1, 512 ladders/GPU, all chains stored",
+                kind="pt", target="three_mixture", dim=50, K=8, units=512, T=2_000, burn_in=0, swap_every=10,
+                var=1.0, F=1122, S=109, bytes=204, proposal="uniform", store="all"),
     "c5": dict(desc="C5 RWM FullRosenbrock d=100, 64 variances x 256 chains (16384 chains/GPU), accumulators only",
                kind="rwm", target="full_rosenbrock", dim=100, K=1, units=16384, T=20_000, burn_in=1000, swap_every=1,
                var=None, F=1895, S=201, bytes=0),
@@ -198,6 +201,9 @@ def build_sampler(wl, dev, rank, store, lanes, seed=2026):
         prop = None
         if wl.get("proposal") == "laplace":
             prop = LaplaceProposal(d, torch.full((d,), wl["var"]), 1.0, torch.device("cpu"), torch.float32)
+        elif wl.get("proposal") == "uniform":
+            from rwm_pt_pytorch_b200.proposal_distributions import UniformRadiusProposal
+            prop = UniformRadiusProposal(d, wl["var"], 1.0, torch.device("cpu"), torch.float32)
         algo = PT(d, wl["var"], t, geom_temp_spacing=True, swap_every=wl["swap_every"], burn_in=wl["burn_in"], device=dev,
                   num_ladders=n, store=store, seed=seed, chain_id_base=rank * n * K, lanes_per_chain=lanes,
                   proposal_distribution=prop, initial_states=np.zeros((n, 1, d), np.float32))
