@@ -882,7 +882,14 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
         slice = (int)(g / (unsigned)a.n_units);
         unit = (long long)(g % (unsigned)a.n_units);
         if (threadIdx.x == 0) {
-          while (*(volatile int*)(a.unit_done + unit) < slice) __nanosleep(256);  // previous slice published?
+          // previous slice published?  Back off up to ~4 us between polls: a slice lasts milliseconds, and a tight poll
+          // (the r1j capture shows 2.5 LDG / NANOSLEEP / BRA per ladder-step from waiting CTAs) competes for issue slots
+          // with the warp that shares the scheduler
+          unsigned ns = 512;
+          while (*(volatile int*)(a.unit_done + unit) < slice) {
+            __nanosleep(ns);
+            ns = ns < 4096 ? ns * 2 : ns;
+          }
           __threadfence();
         }
         __syncthreads();
