@@ -923,18 +923,24 @@ __global__ void __launch_bounds__(kMaxCtaThreads) logp_kernel(const float* __res
   c.leader = c.lane & ~(W - 1);
   Target<E, IEEE> tgt;
   tgt.init(c);
+  // two rows per lane group and iteration: both rows' loads are issued before either density is evaluated (the kernel is
+  // bound by HBM latency x bytes in flight, not by arithmetic)
   const long long stride = (long long)gridDim.x * per_cta;
-  const long long n_round = ((n + stride - 1) / stride) * stride;  // keep warps converged for the shuffles
-  for (long long r = (long long)blockIdx.x * per_cta + cl; r < n_round; r += stride) {
-    const bool ok = r < n;
-    float v[E];
+  const long long n_round = ((n + 2 * stride - 1) / (2 * stride)) * (2 * stride);  // keep warps converged for the shuffles
+  for (long long r = (long long)blockIdx.x * per_cta + cl; r < n_round; r += 2 * stride) {
+    const long long r1 = r + stride;
+    const bool ok0 = r < n, ok1 = r1 < n;
+    float v0[E], v1[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int i = c.base + e;
-      v[e] = (ok && i < d) ? x[r * d + i] : 0.0f;
+      v0[e] = (ok0 && i < d) ? x[r * d + i] : 0.0f;
+      v1[e] = (ok1 && i < d) ? x[r1 * d + i] : 0.0f;
     }
-    const float lp = tgt.logp(v, c);
-    if (ok && c.sub == 0) out[r] = lp;
+    const float lp0 = tgt.logp(v0, c);
+    const float lp1 = tgt.logp(v1, c);
+    if (ok0 && c.sub == 0) out[r] = lp0;
+    if (ok1 && c.sub == 0) out[r1] = lp1;
   }
 }
 
