@@ -389,6 +389,7 @@ def pt_run(spec: Dict, x0, betas, increments, uniforms, swap_uniforms, swap_ever
     decisions = np.zeros((T, L, K), dtype=np.uint8)
     n_rounds = sum(1 for s in range(1, T + 1) if s % swap_every == 0 and s > burn_in)
     swap_dec = np.zeros((max(n_rounds, 1), L, max(K - 1, 1)), dtype=np.uint8)
+    pre_sweep_logp = np.zeros((max(n_rounds, 1), L, K), dtype=np.float32)   # log-densities each sweep started from
     chain = np.zeros((T + 1, L, K, d), dtype=np.float32) if keep_states else None
     logps = np.zeros((T + 1, L, K), dtype=np.float32)
     logps[0] = lp
@@ -416,6 +417,7 @@ def pt_run(spec: Dict, x0, betas, increments, uniforms, swap_uniforms, swap_ever
         if s % swap_every == 0 and s > burn_in and K > 1:
             x = x.copy()
             lp = lp.copy()
+            pre_sweep_logp[r] = lp
             for j in range(K - 1):
                 k = j + 1
                 lsp = swap_log_prob(betas[j], betas[k], lp[:, j], lp[:, k])
@@ -446,7 +448,8 @@ def pt_run(spec: Dict, x0, betas, increments, uniforms, swap_uniforms, swap_ever
         ref_rate = np.where(attempts_at_last_accept > 0, accepts / np.maximum(attempts_at_last_accept, 1), 0.0)
         ref_esjd = np.where(attempts_at_last_accept > 0, sq_beta / np.maximum(attempts_at_last_accept, 1), 0.0)
     return {
-        "decisions": decisions, "swap_decisions": swap_dec[:max(n_rounds, 0)], "chain": chain, "logp": logps,
+        "decisions": decisions, "swap_decisions": swap_dec[:max(n_rounds, 0)],
+        "pre_sweep_logp": pre_sweep_logp[:max(n_rounds, 0)], "chain": chain, "logp": logps,
         "final_state": x, "final_logp": lp,
         "swap_attempts": attempts, "swap_accepts": accepts, "pair_accepts": pair_accepts,
         "attempts_at_last_accept": attempts_at_last_accept,

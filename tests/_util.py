@@ -84,6 +84,8 @@ def make_product_targets():
     d["mvn_identity_d50"] = td.MultivariateNormalTorch(50, device=CPU)
     d["mvn_diag_d6"] = td.MultivariateNormalTorch(
         6, mean=[0.5, -1.0, 0.0, 2.0, 0.25, -0.75], cov=np.diag([0.5, 2.0, 1.0, 4.0, 0.25, 1.5]).tolist(), device=CPU)
+    d["full_rosenbrock_d100"] = td.FullRosenbrockTorch(100, device=CPU)
+    d["neal_funnel_d100"] = td.NealFunnelTorch(100, device=CPU)
     return d
 
 
@@ -114,7 +116,8 @@ def make_keys():
             "three_mixture_pm15_d50", "three_mixture_scaled_d7", "full_rosenbrock_d20", "full_rosenbrock_d3",
             "even_rosenbrock_d10", "even_rosenbrock_d20", "even_rosenbrock_d30", "hybrid_rosenbrock_n3x5",
             "hybrid_rosenbrock_n4x2", "neal_funnel_d10", "neal_funnel_d1", "hypercube_pm1_d5", "hypercube_01_d4",
-            "iid_gamma_d8", "iid_beta_d8", "scaled_mvn_d12", "mvn_identity_d50", "mvn_diag_d6"]
+            "iid_gamma_d8", "iid_beta_d8", "scaled_mvn_d12", "mvn_identity_d50", "mvn_diag_d6", "full_rosenbrock_d100",
+            "neal_funnel_d100"]
 
 
 def specs_equal(a, b):

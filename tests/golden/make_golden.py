@@ -135,6 +135,10 @@ def make_targets():
     d["mvn_identity_d50"] = td.MultivariateNormalTorch(50, device=CPU)
     d["mvn_diag_d6"] = td.MultivariateNormalTorch(
         6, mean=[0.5, -1.0, 0.0, 2.0, 0.25, -0.75], cov=np.diag([0.5, 2.0, 1.0, 4.0, 0.25, 1.5]).tolist(), device=CPU)
+    # BASELINE config 5's shape (13 coordinates x 8 lanes with padding on the CUDA side); unscaled targets draw no randomness,
+    # so appending them leaves every earlier fixture bit-identical
+    d["full_rosenbrock_d100"] = td.FullRosenbrockTorch(100, device=CPU)
+    d["neal_funnel_d100"] = td.NealFunnelTorch(100, device=CPU)
     return d
 
 
@@ -350,6 +354,10 @@ def main():
             proposal=LaplaceProposal(50, torch.full((50,), 2.38 ** 2 / 50), 0.25, CPU, torch.float32))
     gen_rwm("rwm_rough_carpet_d20_uniform", T["rough_carpet_d20"], 400, 50, seed=24,
             proposal=UniformRadiusProposal(20, 2.5, 1.0, CPU, torch.float32))
+
+    # BASELINE config 5: d = 100, at one point of each variance sweep (experiment_RWM_GPU.py:202-218: variance = x^2 / dim)
+    gen_rwm("rwm_full_rosenbrock_d100", T["full_rosenbrock_d100"], 500, 100, seed=25, var=0.340769 ** 2 / 100)
+    gen_rwm("rwm_neal_funnel_d100", T["neal_funnel_d100"], 500, 100, seed=26, var=1.699744 ** 2 / 100)
 
     gen_pt("pt_rough_carpet_d20_geom", T["rough_carpet_d20"], 1000, 200, seed=1, var=0.9, swap_every=10)
     gen_pt("pt_rough_carpet_pm4_d20_se3", T["rough_carpet_pm4_d20"], 300, 0, seed=2, var=2.38 ** 2 / 20, swap_every=3)

@@ -1,0 +1,109 @@
+"""GPU parity tests on the BASELINE configurations' own shapes (run with `-m gpu`):
+
+  C1  RWM / Normal / RoughCarpet (+-15) d=20, 1e5 iterations -- the known answer of the reference's NumPy sampler
+      (algorithms/rwm.py:23-66, seed 1: acceptance 0.250577, ESJD 1.289161) against the CUDA path.
+  C5  FullRosenbrock / NealFunnel d=100, 64 proposal variances x 256 chains on the tuned 13-coordinates x 8-lanes kernel
+      (rosenbrock_torch.py:67-84, funnel_torch.py:39-76, experiment_RWM_GPU.py:202-218), native Philox + fast math,
+      against the NumPy oracle at points of the sweep.
+
+Bars (BASELINE.json north_star): acceptance within 3 Monte-Carlo standard errors, ESJD within 2 %.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rwmpt_oracle as O
+from tests._util import product_target
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _rwm():
+    from rwm_pt_pytorch_b200.algorithms import RandomWalkMH_GPU_Optimized
+    return RandomWalkMH_GPU_Optimized
+
+
+# ---- BASELINE config 1 on the GPU ----------------------------------------------------------------------------
+C1_ACCEPTANCE = 25058 / 100001       # num_acceptances / len(chain): the CPU sampler's denominator counts x0 (rwm.py:36)
+C1_ESJD = 1.289161                   # mean over the 1e5 jumps of the stored chain
+C1_STEPS = 100_000
+
+
+def test_config1_known_answer_on_gpu():
+    """4096 chains x 1e5 steps of the CUDA path on config 1's target / proposal / start (x0 = 0, no burn-in).  The
+    reference value is ONE chain of the NumPy sampler, so its Monte-Carlo error is the spread of single 1e5-step chains,
+    measured here on the kernel's own chains; the mean of 4096 chains adds sd / 64."""
+    dev = _cuda()
+    import rwm_pt_pytorch_b200.target_distributions as td
+    d, B = 20, 4096
+    t = td.RoughCarpetDistributionTorch(d, device=torch.device("cpu"), mode_centers=[-15.0, 0.0, 15.0])
+    algo = _rwm()(d, 2.38 ** 2 / d, t, burn_in=0, device=dev, num_chains=B, seed=1, store="none",
+                  initial_states=np.zeros((B, d)))
+    algo.generate_samples(C1_STEPS)
+    acc = algo.acceptance_rates.cpu().numpy()
+    esjd = algo.esjd_per_chain().cpu().numpy()
+    ref_acc = C1_ACCEPTANCE * (C1_STEPS + 1) / C1_STEPS          # acceptances per step, the kernel's denominator
+    se_acc = acc.std(ddof=1) * np.sqrt(1.0 + 1.0 / B)
+    se_esjd = esjd.std(ddof=1) * np.sqrt(1.0 + 1.0 / B)
+    print(f"[C1] acceptance {acc.mean():.6f} vs {ref_acc:.6f} (single-chain sd {acc.std(ddof=1):.6f}); "
+          f"ESJD {esjd.mean():.6f} vs {C1_ESJD} (single-chain sd {esjd.std(ddof=1):.6f})")
+    assert abs(acc.mean() - ref_acc) <= 3 * se_acc, (acc.mean(), ref_acc, se_acc)
+    assert abs(esjd.mean() - C1_ESJD) <= 0.02 * C1_ESJD, (esjd.mean(), C1_ESJD, se_esjd)
+    # and the same against the oracle's port of the torch path on this configuration (64 chains x 4000 steps)
+    rs = np.random.RandomState(11)
+    B_o, T_o = 64, 4000
+    inc = O.normal_increments(rs.randn(T_o, B_o, d), 2.38 ** 2 / d, 1.0)
+    ora = O.rwm_run(t.spec(), np.zeros((B_o, d), np.float32), 1.0, inc, rs.rand(T_o, B_o), burn_in=0, keep_states=False)
+    short = _rwm()(d, 2.38 ** 2 / d, t, burn_in=0, device=dev, num_chains=B, seed=2, store="none", initial_states=np.zeros((B, d)))
+    short.generate_samples(T_o)
+    a_g, a_o = short.acceptance_rates.cpu().numpy(), ora["acceptance_rate"]
+    e_g, e_o = short.esjd_per_chain().cpu().numpy(), ora["esjd"]
+    assert abs(a_g.mean() - a_o.mean()) <= 3 * np.hypot(a_g.std(ddof=1) / np.sqrt(B), a_o.std(ddof=1) / np.sqrt(B_o))
+    assert abs(e_g.mean() - e_o.mean()) <= 0.02 * e_o.mean() + 3 * np.hypot(e_g.std(ddof=1) / np.sqrt(B), e_o.std(ddof=1) / np.sqrt(B_o))
+
+
+# ---- BASELINE config 5: 64 variances x 256 chains at d = 100 ---------------------------------------------------
+C5_SWEEPS = {"full_rosenbrock_d100": (0.01, 1.0), "neal_funnel_d100": (0.01, 2.5)}   # linspace(0.01, var_max, 64)
+
+
+@pytest.mark.parametrize("key", sorted(C5_SWEEPS))
+def test_config5_variance_sweep_matches_oracle(key):
+    """The whole sweep in ONE launch of the tuned kernel (16384 chains, per-chain proposal std), native Philox + fast
+    math; at six points of the sweep the oracle runs the same configuration with NumPy randomness (128 chains)."""
+    dev = _cuda()
+    d, n_var, per = 100, 64, 256
+    t = product_target(key)
+    spec = t.spec()
+    xs = np.linspace(C5_SWEEPS[key][0], C5_SWEEPS[key][1], n_var)
+    var = np.repeat(xs ** 2 / d, per)
+    T, burn = 3000, 1000
+    np.random.seed(5)
+    algo = _rwm()(d, var, t, burn_in=burn, device=dev, num_chains=n_var * per, seed=2027, store="none")
+    algo._ensure_batch(1)
+    assert algo._batch.geometry() == (13, 8), algo._batch.geometry()      # the tuned C5 mapping is the one under test
+    algo.generate_samples(T - burn)
+    acc = algo.acceptance_rates.cpu().numpy().reshape(n_var, per)
+    esjd = algo.esjd_per_chain().cpu().numpy().reshape(n_var, per)
+    # the curve has the shape the study looks for: acceptance falls monotonically (up to noise), ESJD peaks inside the range
+    am = acc.mean(1)
+    assert am[0] > 0.9 and am[-1] < 0.15 and np.all(np.diff(am) < 0.03)
+    assert 0 < int(np.argmax(esjd.mean(1))) < n_var - 1
+    B_o = 128
+    for i in (2, 8, 16, 26, 40, 60):
+        rs = np.random.RandomState(100 + i)
+        x0 = (1e-8 * rs.randn(B_o, d)).astype(np.float32)
+        inc = O.normal_increments(rs.randn(T, B_o, d), float(xs[i] ** 2 / d), 1.0)
+        ora = O.rwm_run(spec, x0, 1.0, inc, rs.rand(T, B_o), burn_in=burn, keep_states=False)
+        a_o, e_o = ora["acceptance_rate"], ora["esjd"]
+        a_err = np.hypot(acc[i].std(ddof=1) / np.sqrt(per), a_o.std(ddof=1) / np.sqrt(B_o))
+        e_err = np.hypot(esjd[i].std(ddof=1) / np.sqrt(per), e_o.std(ddof=1) / np.sqrt(B_o))
+        print(f"[C5 {key}] x={xs[i]:.4f}: acceptance {acc[i].mean():.5f} vs oracle {a_o.mean():.5f} (3 s.e. {3 * a_err:.5f}); "
+              f"ESJD {esjd[i].mean():.6f} vs {e_o.mean():.6f}")
+        assert abs(acc[i].mean() - a_o.mean()) <= 3 * a_err, (key, i, acc[i].mean(), a_o.mean(), a_err)
+        assert abs(esjd[i].mean() - e_o.mean()) <= 3 * e_err + 0.02 * e_o.mean(), (key, i, esjd[i].mean(), e_o.mean(), e_err)

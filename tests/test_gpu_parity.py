@@ -20,7 +20,9 @@ from tests._util import (load_golden, golden_names, product_target, target_key_o
 pytestmark = pytest.mark.gpu
 
 NEAR_TIE_REL = 2e-5
+NEAR_TIE_BUDGET = 1          # fixtures (out of all rwm_* / pt_* goldens) that may hit a near tie at all; round 1 saw 0
 LOGP_RTOL, LOGP_ATOL = 1e-5, 2e-5
+_NEAR_TIES = []              # golden names whose first decision mismatch was a (verified) near tie
 
 
 def _cuda():
@@ -87,6 +89,8 @@ def test_rwm_injected_matches_reference(name):
     ora = O.rwm_run(spec, g["x0"][None], g["beta"], g["increments"][:, None], g["uniforms"][:, None], burn_in=burn)
     near, hard, until = near_tie_report(dec, g["decisions"][:, None], ora["lar"], g["uniforms"][:, None], NEAR_TIE_REL)
     assert hard == 0, f"{hard} decision mismatches that are not near ties"
+    if near:
+        _NEAR_TIES.append(name)
     n = int(until[0])
     chain = algo.get_chain_gpu().cpu().numpy()
     assert chain.shape == (T + 1, d)
@@ -126,28 +130,42 @@ def test_pt_injected_matches_reference(name):
         assert algo.expected_squared_jump_distance_gpu() == pytest.approx(float(g["cold_esjd"]), rel=1e-5)
         assert len(algo.chain) == T + 1 and algo.step_counter == T
     else:
-        # a near tie somewhere: everything before the first differing step must still agree
+        # A decision differs somewhere.  That is only acceptable at a near tie (|u - p| <= NEAR_TIE_REL p: torch, NumPy and the
+        # shuffle butterfly sum fp32 in different orders, which moves a log-density by an ulp); everything before the first
+        # differing step must still agree exactly, the differing decision must BE a near tie (hard assert, no xfail), and
+        # the whole fixture set may spend at most NEAR_TIE_BUDGET of them (test_near_tie_budget_not_exceeded).
         bad_mh = np.argwhere(dec != g["decisions"])
         bad_sw = np.argwhere(sdec != g["swap_decisions"])
-        first = min([int(bad_mh[0][0])] if len(bad_mh) else [T]) if len(bad_mh) else T
-        if len(bad_sw):
-            rounds = [s for s in range(1, T + 1) if s % se == 0 and s > burn]
-            first = min(first, rounds[int(bad_sw[0][0])] - 1)
-        lar = ora["logp"]  # only used for the message
+        rounds = [s for s in range(1, T + 1) if s % se == 0 and s > burn]
+        first_mh = int(bad_mh[0][0]) if len(bad_mh) else T
+        first_sw = rounds[int(bad_sw[0][0])] - 1 if len(bad_sw) else T
+        first = min(first_mh, first_sw)
         states = torch.stack(algo.get_all_chains_gpu()).cpu().numpy().transpose(1, 0, 2)
         np.testing.assert_array_equal(states[: first + 1], g["states"][: first + 1])
-        if len(bad_mh) and int(bad_mh[0][0]) == first:
+        if first_mh <= first_sw:
             tt, kk = int(bad_mh[0][0]), int(bad_mh[0][1])
             lp_c, lp_p = g["logp"][tt, kk], O.log_density(spec, g["states"][tt, kk] + g["increments"][tt, kk])
             p = np.exp(np.float64(g["betas"][kk]) * (np.float64(lp_p) - np.float64(lp_c)))
-            assert abs(float(g["uniforms"][tt, kk]) - p) <= 10 * NEAR_TIE_REL * p, "decision mismatch that is not a near tie"
-        pytest.xfail(f"near tie at step {first} (documented: fp32 reduction-order ulp); prefix matches exactly")
+            assert abs(float(g["uniforms"][tt, kk]) - p) <= NEAR_TIE_REL * p, "MH decision mismatch that is not a near tie"
+        else:
+            # the sweep's inputs: the reference's recorded post-step log-densities of that step are stored AFTER the sweep,
+            # so recompute the pre-sweep ones from the oracle run (which matches the reference bit for bit, test_oracle_golden)
+            rr, jj = int(bad_sw[0][0]), int(bad_sw[0][1])
+            lpre = ora["pre_sweep_logp"][rr, 0] if "pre_sweep_logp" in ora else None
+            assert lpre is not None, "swap decision mismatch and the oracle records no pre-sweep log-densities"
+            b = np.asarray(g["betas"], np.float64)
+            p = min(1.0, float(np.exp((b[jj] - b[jj + 1]) * (np.float64(lpre[jj + 1]) - np.float64(lpre[jj])))))
+            assert abs(float(g["swap_uniforms"][rr, jj]) - p) <= NEAR_TIE_REL * p, "swap decision mismatch that is not a near tie"
+        _NEAR_TIES.append(name)
 
 
 @pytest.mark.parametrize("case", [
     ("rough_carpet_d20", 20, 0), ("rough_carpet_d20", 20, 8), ("even_rosenbrock_d20", 20, 2), ("even_rosenbrock_d30", 30, 0),
     ("full_rosenbrock_d20", 20, 16), ("three_mixture_pm15_d50", 50, 0), ("neal_funnel_d10", 10, 4), ("hybrid_rosenbrock_n3x5", 11, 0),
     ("iid_gamma_d8", 8, 0), ("iid_beta_d8", 8, 2), ("hypercube_pm1_d5", 5, 1), ("scaled_mvn_d12", 12, 0), ("mvn_diag_d6", 6, 0),
+    # BASELINE config 5's shape: d = 100 on 13 coordinates x 8 lanes (4 padding slots, cross-lane neighbour for Rosenbrock),
+    # per-chain proposal scales like the 64-variance sweep; 16 lanes x 8 as the second mapping
+    ("full_rosenbrock_d100", 100, 0), ("neal_funnel_d100", 100, 0), ("full_rosenbrock_d100", 100, 16), ("neal_funnel_d100", 100, 32),
 ])
 def test_rwm_batch_matches_oracle(case):
     """64 chains x 250 steps with seeded NumPy randomness, every lanes-per-chain mapping exercised."""
@@ -161,7 +179,10 @@ def test_rwm_batch_matches_oracle(case):
     name = t.get_name()
     x0 = np.stack([O.initial_state(name, d, rs) for _ in range(B)]).astype(np.float32)
     scale = {"hypercube_pm1_d5": 0.3, "iid_beta_d8": 0.08, "even_rosenbrock_d20": 0.07, "even_rosenbrock_d30": 0.06,
-             "full_rosenbrock_d20": 0.08, "hybrid_rosenbrock_n3x5": 0.1}.get(key, 0.6)
+             "full_rosenbrock_d20": 0.08, "hybrid_rosenbrock_n3x5": 0.1, "full_rosenbrock_d100": 0.034,
+             "neal_funnel_d100": 0.17}.get(key, 0.6)
+    if d == 100:   # one proposal scale per chain, spanning the sweep's range around its middle
+        scale = scale * np.linspace(0.3, 2.0, B)[None, :, None]
     inc = (rs.randn(T, B, d) * scale).astype(np.float32)
     u = rs.rand(T, B).astype(np.float32)
     betas = np.linspace(1.0, 0.3, B).astype(np.float32)
@@ -267,49 +288,81 @@ def _se_of_rate(p, n_eff):
     return np.sqrt(max(p * (1 - p), 1e-6) / n_eff)
 
 
-@pytest.mark.parametrize("key,d,x,acc_ref,acc_se,esjd_ref,esjd_se", [
-    # seed-averaged curves of the reference's data/ (BASELINE.md section 2): EvenRosenbrock, variance x^2/d, burn-in 1000
-    ("even_rosenbrock_d20", 20, 0.297436, 0.18487, 0.00610, 0.014801, 0.000514),
-    ("even_rosenbrock_d10", 10, 0.161282, 0.45916, 0.01148, 0.010940, 0.000302),
-    ("even_rosenbrock_d30", 30, 0.085641, 0.71921, 0.00227, 0.005212, 0.000017),
+def _shared_stream_se(sd_data, n_data, sd_independent):
+    """Standard error of the mean of the reference's n recorded "seeds".
+
+    The recorded seeds are NOT independent: MCMCSimulation_GPU seeds after constructing the algorithm and the CUDA
+    generator the RWM class draws from is never seeded (rwm_gpu_optimized.py:160-161) -- every
+    seed file of a target consumed the SAME increments and uniforms and differs only in its 1e-8-sized start (20 RoughCarpet
+    "seeds" are identical to the last digit).  Chains driven by common random numbers stay positively correlated, which
+    shows in the files themselves: the seed-to-seed spread is well below the spread of independent chains of the same
+    length (EvenRosenbrock d=30: 0.0122 vs 0.0245).  With pairwise correlation rho, the sample variance estimates
+    sigma^2 (1 - rho) and the variance of the mean is sigma^2 (1 + (n-1) rho) / n = sigma^2 - s^2 (n-1)/n, where sigma is
+    the spread of INDEPENDENT chains -- measured on the kernel's own chains in the same test.  Never below the naive s/sqrt(n).
+    """
+    naive = sd_data ** 2 / n_data
+    return float(np.sqrt(max(sd_independent ** 2 - sd_data ** 2 * (n_data - 1) / n_data, naive)))
+
+
+@pytest.mark.parametrize("key,d,x,n_seeds,acc_ref,acc_sd,esjd_ref,esjd_sd", [
+    # seed-averaged points of the reference's data/*_RWM_GPU_dim*_1000000iters_seed*.json (BASELINE.md section 2): Normal
+    # proposal, variance x^2/d, burn-in 1000, 1e6 iterations; sd = spread over the n seed files
+    ("even_rosenbrock_d20", 20, 0.297436, 24, 0.18487, 0.02987, 0.014801, 0.002517),
+    ("even_rosenbrock_d10", 10, 0.161282, 28, 0.45916, 0.06073, 0.010940, 0.001596),
+    ("even_rosenbrock_d30", 30, 0.085641, 29, 0.71921, 0.01223, 0.005212, 0.000092),
+    # the two families of BASELINE config 5 at the dimension the reference recorded them (d = 20)
+    ("full_rosenbrock_d20", 20, 0.340769, 20, 0.51297, 0.00485, 0.057184, 0.000578),
+    ("neal_funnel_d20", 20, 1.699744, 30, 0.35467, 0.06318, 0.981295, 0.176041),
 ])
-def test_native_rng_matches_reference_statistics(key, d, x, acc_ref, acc_se, esjd_ref, esjd_se):
-    """256 chains x 1e6 steps (the reference's own run length) against the reference's recorded runs; its s.e. over
-    ~25 seed files is the dominant uncertainty."""
+def test_native_rng_matches_reference_statistics(key, d, x, n_seeds, acc_ref, acc_sd, esjd_ref, esjd_sd):
+    """256 chains x 1e6 steps (the reference's own run length and start) against the reference's recorded runs:
+    acceptance within 3 standard errors, ESJD within 2 % (+ 3 s.e.), no further slack.  The standard error of the recorded
+    mean accounts for the seeds sharing one random stream (_shared_stream_se)."""
     dev = _cuda()
     RWM, _ = _algs()
-    t = product_target(key)
+    if key == "neal_funnel_d20":
+        import rwm_pt_pytorch_b200.target_distributions as td
+        t = td.NealFunnelTorch(20, device=torch.device("cpu"))
+    else:
+        t = product_target(key)
     np.random.seed(7)
     algo = RWM(d, x * x / d, t, burn_in=1000, device=dev, num_chains=256, seed=12345)
     algo.generate_samples(1_000_000)
     acc = algo.acceptance_rates.cpu().numpy()
     esjd = algo.esjd_per_chain().cpu().numpy()
     acc_mean, esjd_mean = acc.mean(), esjd.mean()
-    acc_err = np.hypot(acc.std(ddof=1) / np.sqrt(len(acc)), acc_se)
-    esjd_err = np.hypot(esjd.std(ddof=1) / np.sqrt(len(esjd)), esjd_se)
-    # The data/ chains are still in their transient at 1e6 steps (tests/golden/make_oracle_transient_stats.py: the NumPy
-    # port of the reference itself drifts from 0.80 at 2e5 steps to 0.727 at 1e6 for d=30), so their seed-to-seed s.e.
-    # understates the uncertainty of the pooled rate: 1.5 % relative slack on top of the 3 s.e.
-    assert abs(acc_mean - acc_ref) <= 3 * acc_err + 0.015 * acc_ref, (acc_mean, acc_ref, acc_err)
+    acc_err = np.hypot(acc.std(ddof=1) / np.sqrt(len(acc)), _shared_stream_se(acc_sd, n_seeds, acc.std(ddof=1)))
+    esjd_err = np.hypot(esjd.std(ddof=1) / np.sqrt(len(esjd)), _shared_stream_se(esjd_sd, n_seeds, esjd.std(ddof=1)))
+    print(f"[data/ {key}] acc {acc_mean:.5f} vs {acc_ref} (3 s.e. = {3 * acc_err:.5f}); esjd {esjd_mean:.6f} vs {esjd_ref} "
+          f"(3 s.e. = {3 * esjd_err:.6f}); independent-chain sd {acc.std(ddof=1):.5f} vs seed-file sd {acc_sd}")
+    assert abs(acc_mean - acc_ref) <= 3 * acc_err, (acc_mean, acc_ref, acc_err)
     assert abs(esjd_mean - esjd_ref) <= 3 * esjd_err + 0.02 * esjd_ref, (esjd_mean, esjd_ref, esjd_err)
 
 
-def test_native_rng_matches_oracle_run_in_transient():
-    """Same configuration as the d=30 data/ point, against a 384-chain 1e6-step run of the NumPy oracle (recorded by
-    tests/golden/make_oracle_transient_stats.py): acceptance within 3 standard errors at 1e6 steps."""
+@pytest.mark.parametrize("d", [10, 20, 30])
+def test_native_rng_matches_oracle_run_in_transient(d):
+    """The three EvenRosenbrock data/ points against 384-chain 1e6-step runs of the NumPy oracle -- the reference ALGORITHM
+    with independent streams, same start, same length (recorded by tests/golden/make_oracle_transient_stats.py):
+    acceptance within 3 standard errors and ESJD within 2 % (+ 3 s.e.) at 1e6 steps, where the chains are still in their
+    transient (d=30: 0.80 at 2e5 steps -> 0.727 at 1e6)."""
     import json
     dev = _cuda()
     RWM, _ = _algs()
-    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_even_rosenbrock_d30.json")) as f:
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"oracle_even_rosenbrock_d{d}.json")) as f:
         rec = json.load(f)
     ref, ref_se = rec["acceptance_at_steps"]["1000000"]
-    d, x = 30, rec["config"]["x"]
+    x = rec["config"]["x"]
     np.random.seed(7)
-    algo = RWM(d, x * x / d, product_target("even_rosenbrock_d30"), burn_in=1000, device=dev, num_chains=1024, seed=99)
+    algo = RWM(d, x * x / d, product_target(f"even_rosenbrock_d{d}"), burn_in=1000, device=dev, num_chains=1024, seed=99)
     algo.generate_samples(1_000_000)
     acc = algo.acceptance_rates.cpu().numpy()
     err = np.hypot(acc.std(ddof=1) / np.sqrt(len(acc)), ref_se)
     assert abs(acc.mean() - ref) <= 3 * err, (acc.mean(), ref, err)
+    if "esjd_at_steps" in rec:
+        eref, eref_se = rec["esjd_at_steps"]["1000000"]
+        esjd = algo.esjd_per_chain().cpu().numpy()
+        eerr = np.hypot(esjd.std(ddof=1) / np.sqrt(len(esjd)), eref_se)
+        assert abs(esjd.mean() - eref) <= 3 * eerr + 0.02 * eref, (esjd.mean(), eref, eerr)
 
 
 @pytest.mark.parametrize("d,lanes", [(20, 0), (30, 0), (10, 0), (7, 0), (20, 2), (50, 0)])
@@ -969,3 +1022,9 @@ def test_batched_sweep_drivers_write_the_reference_schema(tmp_path):
                       out_dir=str(tmp_path))
     assert {'max_actual_acceptance_rate', 'max_constr_acceptance_rate', 'swap_acceptance_rates_range'} <= set(pt)
     assert len(pt['acceptance_rates']) == 3 and pt['acceptance_rates'][0] < pt['acceptance_rates'][-1]
+
+
+def test_near_tie_budget_not_exceeded():
+    """Runs after the golden tests of this module: at most NEAR_TIE_BUDGET fixtures may have met a near tie (each one was
+    verified to BE a near tie by the test that recorded it)."""
+    assert len(_NEAR_TIES) <= NEAR_TIE_BUDGET, _NEAR_TIES
