@@ -14,7 +14,8 @@
  *     caller, the work is enqueued on `cuda_stream` (a cudaStream_t cast to void*; NULL = default
  *     stream) and the call returns without synchronising;
  *   - return value 0 = ok, negative = error (RWMPT_E*); rwmpt_last_error() gives a thread-local text;
- *   - no global mutable state: re-entrant, any number of streams / devices;
+ *   - re-entrant, any number of streams / devices; the only process-wide state is one atomic bit per device that
+ *     remembers rwmpt_run_host has raised the device memory pool's release threshold;
  *   - all floating point data is IEEE binary32 unless stated.
  */
 #ifndef RWMPT_H_
@@ -193,9 +194,11 @@ int rwmpt_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 /*
  * Host-buffer convenience entry: every pointer in `args` that is non-NULL is a HOST pointer; the call
- * allocates device buffers, copies in, runs rwmpt_pt_run, copies state / logp / accumulators / samples /
- * decisions back and synchronises.  `device` is the CUDA ordinal.  This is the end-to-end call the
- * benchmark times (`e2e`).  h2d_bytes / d2h_bytes (nullable) receive the bytes moved.
+ * allocates device buffers, copies in, runs rwmpt_pt_run, copies state / logp / accumulators / decisions and the
+ * retained-sample rows THIS call wrote back (rows returned by earlier calls of a resumed run, and rows beyond
+ * sample_rows, are left untouched on the host) and synchronises.  `device` is the CUDA ordinal; the caller's current
+ * device is restored.  This is the end-to-end call the benchmark times (`e2e`).  h2d_bytes / d2h_bytes (nullable)
+ * receive the bytes moved.
  */
 int rwmpt_run_host(const rwmpt_run_args_t* args, int32_t device, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 

@@ -61,6 +61,7 @@ class LadderBatch:
         self.store_mode = _lib.STORE_NONE
         self.thin = 1
         self.capacity = 0
+        self.store_origin = 0     # global step the sample buffer's row 0 corresponds to (see rewind_storage)
 
     # ------------------------------------------------------------------------------------------------
     def _target_struct(self):
@@ -110,7 +111,19 @@ class LadderBatch:
         """Rows of the sample buffer that hold data (initial state + retained steps), capped at capacity."""
         if self.samples is None:
             return 0
-        return min(1 + self.total_steps // self.thin, self.capacity)
+        return min(1 + (self.total_steps - self.store_origin) // self.thin, self.capacity)
+
+    def rewind_storage(self):
+        """Start filling the sample buffer from row 0 again: row 0 <- the current state, later rows <- the steps that
+        follow (`store_start` of include/rwmpt.h).  Lets a long run stream trajectories through a fixed-size buffer, one
+        launch per buffer-full (the benchmark's stored-trajectory workloads re-use one buffer for every timed launch)."""
+        if self.samples is None:
+            return
+        self.store_origin = self.total_steps
+        src = self.state if self.store_mode == _lib.STORE_ALL else self.state.view(self.L, self.K, self.dim)[:, 0]
+        self.samples[:, 0] = src
+        if self.sample_logp is not None:
+            self.sample_logp[:, 0] = self.logp if self.store_mode == _lib.STORE_ALL else self.logp.view(self.L, self.K)[:, 0]
 
     # ------------------------------------------------------------------------------------------------
     def run(self, n_steps: int, inj_increments=None, inj_uniforms=None, inj_swap_uniforms=None,
@@ -133,7 +146,7 @@ class LadderBatch:
         a.seed = self.ensure_seed() if inj_increments is None else 0
         a.chain_id_base = self.chain_id_base
         a.store_mode, a.math_mode = self.store_mode, self.math_mode
-        a.store_start, a.thin = 0, self.thin
+        a.store_start, a.thin = self.store_origin, self.thin
         if self.samples is not None:
             # row 0 of the buffer is the initial state: hand the kernel a pointer to row 1
             a.samples = self.samples.data_ptr() + 4 * self.dim

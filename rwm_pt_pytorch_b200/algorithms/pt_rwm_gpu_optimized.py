@@ -52,7 +52,7 @@ class ParallelTemperingRWM_GPU_Optimized(MHAlgorithm):
                  seed: Optional[int] = None,
                  store: Optional[str] = None,
                  thin: int = 1,
-                 swap_mode: str = "reference",
+                 swap_mode: Optional[str] = None,
                  math_mode: str = "fast",
                  proposal_distribution: ProposalDistribution = None,
                  initial_states=None,
@@ -111,7 +111,12 @@ class ParallelTemperingRWM_GPU_Optimized(MHAlgorithm):
         if store not in ("all", "cold", "none"):
             raise ValueError("store must be 'all', 'cold' or 'none'")
         self.store = store
-        self.swap_mode = swap_mode
+        # None = the reference's semantics (parity with its recorded numbers), with a one-time warning on the first
+        # native-RNG run: that "swap" copies k -> j and does not leave the target invariant (see _warn_copy_swap)
+        self._swap_mode_defaulted = swap_mode is None
+        self.swap_mode = "reference" if swap_mode is None else swap_mode
+        if self.swap_mode not in _lib.SWAP_MODES:
+            raise ValueError("swap_mode must be 'reference' or 'exchange'")
         self.math_mode = math_mode
         self.seed = seed
         self.chain_id_base = chain_id_base
@@ -136,6 +141,22 @@ class ParallelTemperingRWM_GPU_Optimized(MHAlgorithm):
         self._chain_cache = None
         self._batch: Optional[LadderBatch] = None
         self._make_batch()
+
+    _copy_swap_warned = False
+
+    def _warn_copy_swap(self):
+        """The reference's accepted "swap" is a copy: chain j receives chain k's state and k keeps its own
+        (pt_rwm_gpu_optimized.py:50-59 on tensor views).  It is the default here because every
+        recorded PT number of the reference was produced with it, but the cold chain it yields is biased (RoughCarpet
+        mode weights .455/.310/.234 instead of .5/.3/.2).  Say so once per process when the caller
+        did not choose a mode."""
+        cls = ParallelTemperingRWM_GPU_Optimized
+        if self._swap_mode_defaulted and not cls._copy_swap_warned:
+            cls._copy_swap_warned = True
+            warnings.warn("ParallelTemperingRWM_GPU_Optimized runs with swap_mode='reference': an accepted swap copies the "
+                          "hotter chain's state into the colder one (what the reference does) and does not leave the target "
+                          "invariant. Pass swap_mode='exchange' for textbook parallel tempering, or swap_mode='reference' "
+                          "explicitly to silence this warning.", stacklevel=3)
 
     # ---- ladder construction ---------------------------------------------------------------------------
     def _construct_geometric_ladder(self):
@@ -295,6 +316,7 @@ class ParallelTemperingRWM_GPU_Optimized(MHAlgorithm):
     def step(self, step_index: int = None):
         """One Metropolis step of all chains, plus the swap sweep when due (:541-574)."""
         b = self._require_batch()
+        self._warn_copy_swap()
         if self.store != "none" and b.samples is None:
             b.allocate_storage(self.store, b.total_steps // self.thin + 2, self.thin)
         elif b.samples is not None and not self.pre_allocate_steps:
@@ -307,6 +329,7 @@ class ParallelTemperingRWM_GPU_Optimized(MHAlgorithm):
         samples (:761-770): (num_samples, dim), or (num_ladders, num_samples, dim) for a batch of ladders, or an
         empty tensor with store='none'."""
         b = self._require_batch()
+        self._warn_copy_swap()
         total = self.burn_in + int(num_samples)                         # :707
         if self.store != "none":
             need = (b.total_steps + total) // self.thin + 1

@@ -90,6 +90,12 @@ class RandomWalkMH_GPU_Optimized(MHAlgorithm):
         if var_arr is not None and isinstance(self.proposal_dist, NormalProposal):
             vars_ = np.broadcast_to(var_arr, (self.num_chains,)).astype(np.float64)
             scales = np.sqrt((vars_ / betas).astype(np.float32)).astype(np.float32)     # normal.py:27-31
+        elif (beta_arr.ndim == 0 and torch.device(self.proposal_dist.device).type == self.device.type
+              and self.proposal_dist.dtype == self.dtype):
+            # a supplied proposal that already lives on the sampler's device / dtype is used AS IS by the reference, i.e.
+            # with the proposal's own beta (rwm_gpu_optimized.py:209-212); only a proposal on another device / dtype is
+            # rebuilt with the sampler's beta (:165-208)
+            scales = np.full(self.num_chains, self.proposal_dist._sample_scale(), dtype=np.float32)
         else:
             scales = np.asarray([self.proposal_dist.chain_scale(float(b)) for b in betas], dtype=np.float32)
         if proposal_scales is not None:

@@ -1,6 +1,7 @@
 // rwmpt_api.cu -- the extern "C" boundary of librwmpt.so (see include/rwmpt.h): argument validation,
 // launch geometry, family dispatch, and the small stand-alone kernels (proposal sampler, PT swap sweep,
 // ESJD reduction, Philox known-answer hook) plus the host-buffer end-to-end entry.
+#include <atomic>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -172,6 +173,10 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   const bool inject = r->inj_increments != nullptr;
   if (inject != (r->inj_uniforms != nullptr)) return fail(RWMPT_EINVAL, "inj_increments and inj_uniforms go together");
   if (!inject && !r->prop_scale) return fail(RWMPT_EINVAL, "prop_scale is required unless increments are injected");
+  // a run with injected increments has no Philox stream of its own (the facade passes seed 0): the sweep's uniforms must
+  // be injected too, otherwise the two sweep forms (shuffle / shared memory) would fall back to different sources
+  if (inject && r->n_temps > 1 && !r->inj_swap_uniforms && count_rounds(r->step_offset, r->n_steps, r->burn_in, r->swap_every) > 0)
+    return fail(RWMPT_EINVAL, "inj_increments on a ladder (n_temps > 1) needs inj_swap_uniforms as well");
   if (r->samples) {
     if (r->store_mode != RWMPT_STORE_COLD && r->store_mode != RWMPT_STORE_ALL)
       return fail(RWMPT_EINVAL, "samples given but store_mode is NONE");
@@ -730,13 +735,20 @@ struct DevBuf {
   size_t bytes = 0;
   void* host = nullptr;
   bool out = false;
+  size_t pitch = 0, row_off = 0, width = 0;  // pitch != 0: copied back as a 2-D block of rows (retained samples)
 };
 }  // namespace
 
 int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
   if (!r) return fail(RWMPT_EINVAL, "args is NULL");
+  int prev_device = -1;
+  cudaGetDevice(&prev_device);  // restored before returning: the entry must not change the caller's current device
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  struct RestoreDevice {
+    int dev;
+    ~RestoreDevice() { if (dev >= 0) cudaSetDevice(dev); }
+  } restore{prev_device};
   const int64_t d = r->target.dim, K = r->n_temps;
   if (d < 1 || K < 1 || r->n_ladders < 0 || r->n_steps < 0) return fail(RWMPT_EINVAL, "bad sizes");
   const int64_t n_chains = r->n_ladders * K;
@@ -749,12 +761,32 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
   e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   int rc = RWMPT_OK;
+  // Retained-sample rows THIS call writes: global step s is retained as row (s - store_start) / thin - 1 when
+  // s > store_start and (s - store_start) % thin == 0; this call runs steps (step_offset, step_offset + n_steps].  Only
+  // those rows are copied back (one 2-D copy per buffer: `stored_chains` segments, one per chain), so the rows earlier
+  // calls of a resumed run returned -- and rows at or beyond sample_rows -- are never overwritten on the host with
+  // device memory this call did not write.
+  int64_t row_lo = 0, row_hi = 0;
+  if (r->samples && r->thin >= 1) {
+    const int64_t before = r->step_offset > r->store_start ? (r->step_offset - r->store_start) / r->thin : 0;
+    const int64_t upto = r->step_offset + r->n_steps > r->store_start ? (r->step_offset + r->n_steps - r->store_start) / r->thin : 0;
+    row_lo = before < r->sample_rows ? before : r->sample_rows;
+    row_hi = upto < r->sample_rows ? upto : r->sample_rows;
+  }
   // one device arena for every staged buffer (a single stream-ordered allocation per call), 256-byte aligned slices
-  struct Want { const void* host; size_t bytes; bool in, out; void** slot; };
+  struct Want { const void* host; size_t bytes; bool in, out; void** slot; size_t pitch, row_off, width; };
   std::vector<Want> wants;
   auto stage = [&](const void* host, size_t bytes, bool in, bool out, void** slot) {
     *slot = nullptr;
-    if (host && bytes) wants.push_back({host, bytes, in, out, slot});
+    if (host && bytes) wants.push_back({host, bytes, in, out, slot, 0, 0, 0});
+  };
+  // out-only, copied back as `stored_chains` segments of rows [row_lo, row_hi): pitch / offset / width in bytes
+  auto stage_rows = [&](const void* host, size_t row_bytes, void** slot) {
+    *slot = nullptr;
+    const size_t bytes = row_bytes * (size_t)stored_chains * (size_t)r->sample_stride;
+    if (host && bytes)
+      wants.push_back({host, bytes, false, row_hi > row_lo, slot, row_bytes * (size_t)r->sample_stride, row_bytes * (size_t)row_lo,
+                       row_bytes * (size_t)(row_hi - row_lo)});
   };
   stage(r->target.params, sizeof(float) * r->target.n_params, true, false, (void**)&a.target.params);
   stage(r->prop_scale, sizeof(float) * n_chains, true, false, (void**)&a.prop_scale);
@@ -762,8 +794,8 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
   stage(r->beta, sizeof(float) * n_chains, true, false, (void**)&a.beta);
   stage(r->state, sizeof(float) * n_chains * d, true, true, (void**)&a.state);
   stage(r->logp, sizeof(float) * n_chains, true, true, (void**)&a.logp);
-  stage(r->samples, sizeof(float) * stored_chains * r->sample_stride * d, false, true, (void**)&a.samples);
-  stage(r->sample_logp, sizeof(float) * stored_chains * r->sample_stride, false, true, (void**)&a.sample_logp);
+  stage_rows(r->samples, sizeof(float) * d, (void**)&a.samples);
+  stage_rows(r->sample_logp, sizeof(float), (void**)&a.sample_logp);
   stage(r->accept_count, 8 * n_chains, true, true, (void**)&a.accept_count);
   stage(r->sq_jump_sum, 8 * n_chains, true, true, (void**)&a.sq_jump_sum);
   stage(r->swap_accepts, 8 * r->n_ladders * (K > 1 ? K - 1 : 0), true, true, (void**)&a.swap_accepts);
@@ -771,6 +803,7 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
   stage(r->inj_increments, sizeof(float) * r->n_steps * n_chains * d, true, false, (void**)&a.inj_increments);
   stage(r->inj_uniforms, sizeof(float) * r->n_steps * n_chains, true, false, (void**)&a.inj_uniforms);
   stage(r->inj_swap_uniforms, sizeof(float) * rounds * r->n_ladders * (K - 1), true, false, (void**)&a.inj_swap_uniforms);
+  // decision outputs: the kernel writes every element of both (one flag per step and chain / per sweep and pair)
   stage(r->decisions, (size_t)r->n_steps * n_chains, false, true, (void**)&a.decisions);
   stage(r->swap_decisions, (size_t)rounds * r->n_ladders * (K > 1 ? K - 1 : 0), false, true, (void**)&a.swap_decisions);
   size_t total = 0;
@@ -780,14 +813,16 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
     // stream-ordered allocation from the device's default pool, which keeps its memory between calls (release threshold
     // raised once per device): after the first call this is a pool hit, not a cudaMalloc / cudaFree pair that
     // serialises against every other process and context on the node
-    static bool pool_kept[64] = {};
-    if (device >= 0 && device < 64 && !pool_kept[device]) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    static std::atomic<unsigned long long> pool_kept{0ull};   // bit per device; the only process-wide state of the library
+    if (device >= 0 && device < 64) {
+      const unsigned long long bit = 1ull << device;
+      if (!(pool_kept.fetch_or(bit) & bit)) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+          unsigned long long keep = ~0ull;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
       }
-      pool_kept[device] = true;
     }
     e = cudaMallocAsync((void**)&arena, total, st);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync");
@@ -797,6 +832,7 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
     if (rc) break;
     DevBuf b;
     b.p = arena + off; b.bytes = w.bytes; b.host = const_cast<void*>(w.host); b.out = w.out;
+    b.pitch = w.pitch; b.row_off = w.row_off; b.width = w.width;
     off += (w.bytes + 255) & ~(size_t)255;
     *w.slot = b.p;
     if (w.in) {
@@ -810,9 +846,15 @@ int rwmpt_run_host(const rwmpt_run_args_t* r, int32_t device, uint64_t* h2d_byte
   if (!rc) {
     for (auto& b : bufs) {
       if (!b.out) continue;
-      e = cudaMemcpyAsync(b.host, b.p, b.bytes, cudaMemcpyDeviceToHost, st);
+      if (b.pitch) {
+        e = cudaMemcpy2DAsync((char*)b.host + b.row_off, b.pitch, (char*)b.p + b.row_off, b.pitch, b.width, (size_t)stored_chains,
+                              cudaMemcpyDeviceToHost, st);
+        d2h += b.width * (size_t)stored_chains;
+      } else {
+        e = cudaMemcpyAsync(b.host, b.p, b.bytes, cudaMemcpyDeviceToHost, st);
+        d2h += b.bytes;
+      }
       if (e != cudaSuccess) { rc = cuda_fail(e, "D2H copy"); break; }
-      d2h += b.bytes;
     }
   }
   if (arena) cudaFreeAsync(arena, st);

@@ -309,7 +309,7 @@ template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, b
 __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long cta, const long long step_offset,
                                           const long long n_steps, const long long rounds_before) {
   using M = Mth<IEEE>;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];  // staged rows are flushed as float4 / float2 vectors
 
   const int W = WT > 0 ? WT : a.W;
   const int K = a.K, d = a.dim;

@@ -81,7 +81,10 @@ cudaError_t launch_mcmc_store(const KernelArgs& a_in, const LaunchGeom& g, cudaS
         e = cudaMallocAsync((void**)&ws, bytes, st);
         if (e != cudaSuccess) return e;
         e = cudaMemsetAsync(ws, 0, bytes, st);
-        if (e != cudaSuccess) return e;
+        if (e != cudaSuccess) {
+          cudaFreeAsync(ws, st);
+          return e;
+        }
         a.ticket = ws;
         a.unit_done = reinterpret_cast<int*>(ws + 1);
         kern<<<(unsigned)P, g.threads, g.smem, st>>>(a);

@@ -981,6 +981,85 @@ def test_host_buffer_entry_matches_device_path():
     assert h2d.value > 0 and d2h.value >= state.nbytes
 
 
+@pytest.mark.parametrize("store", ["all", "cold"])
+def test_host_buffer_entry_resumed_with_samples_keeps_earlier_rows(store):
+    """rwmpt_run_host with retained samples over two resumed calls (odd split, thinning, capacity smaller than the run):
+    each call copies back only the rows it wrote, so the rows of the first call survive the second, rows beyond
+    sample_rows keep their sentinel, and the result equals LadderBatch.run on device buffers."""
+    import ctypes as C
+    from rwm_pt_pytorch_b200 import _lib
+    dev = _cuda()
+    _, PT = _algs()
+    t = product_target("rough_carpet_d20")
+    L, K, d, thin = 6, 8, 20, 3
+    T1, T2, burn = 101, 160, 10
+    algo = PT(d, 0.9, t, geom_temp_spacing=True, swap_every=10, burn_in=burn, device=dev, num_ladders=L, store=store, thin=thin,
+              seed=77, pre_allocate_steps=10_000)
+    b = algo._batch
+    lp0 = b.logp.cpu().numpy().copy()
+    b.run(T1); b.run(T2)
+    torch.cuda.synchronize()
+    rows_total = (T1 + T2) // thin
+    dev_samples = b.samples.cpu().numpy()[:, 1:1 + rows_total]            # row 0 of the facade's buffer is the initial state
+    dev_slp = b.sample_logp.cpu().numpy()[:, 1:1 + rows_total]
+    lib = _lib.load()
+    params = t.pack().numpy().copy()
+    n_stored = L * K if store == "all" else L
+    stride, cap_rows = rows_total + 5, rows_total - 4                       # the last 4 retained rows do not fit: dropped
+    SENT = np.float32(-777.0)
+    samples = np.full((n_stored, stride, d), SENT, np.float32)
+    slp = np.full((n_stored, stride), SENT, np.float32)
+    state = np.zeros((L * K, d), np.float32); logp = lp0.copy()
+    beta = np.tile(np.asarray(algo.beta_ladder, np.float32), L); scale = np.tile(algo._scales, L)
+    acc = np.zeros(L * K, np.uint64); sq = np.zeros(L * K, np.float64)
+    sacc = np.zeros((L, K - 1), np.uint64); last = np.zeros(L * K, np.uint64)
+    a = _lib.RunArgs()
+    a.target = _lib.TargetT(t.family_id, d, params.ctypes.data, params.size)
+    a.proposal_family, a.n_temps = 0, K
+    a.prop_scale, a.beta = scale.ctypes.data, beta.ctypes.data
+    a.n_ladders, a.burn_in = L, burn
+    a.swap_every, a.swap_mode = 10, 0
+    a.state, a.logp = state.ctypes.data, logp.ctypes.data
+    a.seed = 77
+    a.samples, a.sample_logp = samples.ctypes.data, slp.ctypes.data
+    a.store_mode = _lib.STORE_MODES[store]
+    a.store_start, a.thin, a.sample_stride, a.sample_rows = 0, thin, stride, cap_rows
+    a.accept_count, a.sq_jump_sum = acc.ctypes.data, sq.ctypes.data
+    a.swap_accepts, a.swap_last_attempt = sacc.ctypes.data, last.ctypes.data
+    prev = torch.cuda.current_device()
+    d2h_seen = []
+    for off, n in ((0, T1), (T1, T2)):
+        a.step_offset, a.n_steps = off, n
+        h2d, d2h = C.c_uint64(), C.c_uint64()
+        _lib.check(lib.rwmpt_run_host(C.byref(a), 0, C.byref(h2d), C.byref(d2h)))
+        d2h_seen.append(d2h.value)
+        if off == 0:
+            first_rows = T1 // thin
+            np.testing.assert_array_equal(samples[:, :first_rows], dev_samples[:, :first_rows])
+            assert (samples[:, first_rows:] == SENT).all()                 # nothing beyond the rows this call wrote
+    assert torch.cuda.current_device() == prev
+    np.testing.assert_array_equal(samples[:, :cap_rows], dev_samples[:, :cap_rows])
+    np.testing.assert_array_equal(slp[:, :cap_rows], dev_slp[:, :cap_rows])
+    assert (samples[:, cap_rows:] == SENT).all() and (slp[:, cap_rows:] == SENT).all()
+    np.testing.assert_array_equal(state, b.state.cpu().numpy())
+    np.testing.assert_array_equal(acc.astype(np.int64), b.accept_count.cpu().numpy())
+    # the second call moved only its own rows back (plus state / log-density / accumulators)
+    rows2 = cap_rows - T1 // thin
+    fixed = state.nbytes + logp.nbytes + acc.nbytes + sq.nbytes + sacc.nbytes + last.nbytes
+    assert d2h_seen[1] == fixed + n_stored * rows2 * (d + 1) * 4
+
+
+def test_injected_increments_on_a_ladder_need_injected_swap_uniforms():
+    """without them the shuffle sweep and the shared-memory sweep would draw from different sources."""
+    dev = _cuda()
+    _, PT = _algs()
+    t = product_target("rough_carpet_d20")
+    algo = PT(20, 0.9, t, geom_temp_spacing=True, swap_every=2, device=dev, num_ladders=2, store="none", math_mode="ieee")
+    inc = np.zeros((4, 16, 20), np.float32)
+    with pytest.raises(ValueError, match="inj_swap_uniforms"):
+        algo._batch.run(4, inj_increments=inc, inj_uniforms=np.zeros((4, 16), np.float32), want_decisions=True)
+
+
 def test_iterative_ladder_construction_runs_on_gpu_densities():
     dev = _cuda()
     _, PT = _algs()
