@@ -1,12 +1,28 @@
-# One GPU session: packed-fp32 probe, parity tests, then C3 / C2 A/B over the variant libs that exist.
-#   VARIANTS="'' _nox2 _exp2" bash scripts/gpu_round.sh
+# One GPU session: parity tests, the default bench line (all BASELINE configs + reference baselines), the reference arm,
+# and the ncu launch list of the same command.
+#   [SKIP_TESTS=1] [BENCH_ARGS="--quick"] bash scripts/gpu_round.sh <tag>
+TAG=${1:-r2}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/gpu.txt
-[ -x scripts/probes/f32x2_probe ] && timeout 300 scripts/probes/f32x2_probe > gpurun_out/f32x2_probe.log 2>&1
+nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/gpu_$TAG.txt
 if [ -z "$SKIP_TESTS" ]; then
-timeout 1200 python -m pytest tests -m gpu -x -q -W ignore > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
+  timeout 2400 python -m pytest tests -m gpu -x -q -W ignore -s > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_$TAG.log
+  grep -E "^\[|passed|failed|error|pytest exit" gpurun_out/pytest_gpu_$TAG.log | tail -40
 fi
-for v in ${VARIANTS:-main}; do [ "$v" = main ] && v=""; lib=$PWD/rwm_pt_pytorch_b200/librwmpt$v.so; [ -f $lib ] || continue
- for wl in ${WORKLOADS:-c3 c2}; do echo -n "variant[$v] $wl: "; RWMPT_LIB=$lib timeout 600 python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu --no-e2e --T ${T:-100000} 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], round(d['roofline']['frac'],4), d['acceptance_rate'], d.get('swap_acceptance_rate'), d['esjd'])"; done; done 2>&1 | tee gpurun_out/ab_round.log
-# schedule A/B on the main library: plain (1) vs auto (0)
-for sc in ${SCHEDULES:-}; do for wl in ${WORKLOADS:-c3 c2}; do echo -n "schedule[$sc] $wl: "; RWMPT_SCHEDULE=$sc timeout 600 python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu --no-e2e --T ${T:-100000} 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], round(d['roofline']['frac'],4), d['acceptance_rate'], d.get('swap_acceptance_rate'), d['esjd'])"; done; done 2>&1 | tee gpurun_out/ab_sched.log
+timeout 1500 python bench.py --steps 5 --warmup 3 $BENCH_ARGS > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"; tail -c 1500 gpurun_out/bench_$TAG.err
+python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/bench_$TAG.json").read().strip().splitlines()[-1])
+    print("C3", d["value"], d["roofline"]["frac"], "e2e", d.get("e2e", {}).get("value"), "clocks", d["clocks"])
+    print("cpu_baseline", d.get("cpu_baseline", {}).get("value"), d.get("cpu_baseline", {}).get("kind"), "torch", {k: v.get("chain_steps_per_s") for k, v in d.get("reference_torch", {}).items() if isinstance(v, dict)})
+    for k, v in d.get("also", {}).items():
+        print(k, v["value"], v["roofline"]["bound"], round(v["roofline"]["frac"], 4), "e2e", v.get("e2e", {}).get("value"), v.get("note"))
+except Exception as e:
+    print("bench parse failed", e)
+PY
+if [ -z "$SKIP_REF" ]; then
+  timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; tail -c 700 gpurun_out/bench_ref_$TAG.json
+fi
+if [ -z "$SKIP_NCU" ]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-aux --also none > gpurun_out/ncu_list_$TAG.log 2>&1; tail -3 gpurun_out/launches_$TAG.csv
+fi
