@@ -160,6 +160,17 @@ int rwmpt_pick_geometry(const rwmpt_run_args_t* args, int32_t* lanes_per_chain, 
 int rwmpt_log_density(const rwmpt_target_t* target, const float* x, int64_t n, float* out, int32_t math_mode,
                       void* cuda_stream);
 
+/* Swap-probability estimate of the iterative temperature-ladder construction, replaces the inner estimate of
+ * _construct_iterative_ladder (algorithms/pt_rwm_gpu_optimized.py:356-368) together with the targets' heuristic tempered
+ * samplers draw_samples_torch (multimodal_torch.py:270-333, 532-565; rosenbrock_torch.py:224-248;
+ * multivariate_normal_torch.py:101-121, 249-268):
+ *   *sum_out += sum_{r < n} min(1, exp((beta_curr - beta_star) (log pi(x*_r) - log pi(x_r)))),
+ * x_r ~ sampler(beta_curr), x*_r ~ sampler(beta_star), Philox subsequence row_id_base + r.  sum_out is a DEVICE double
+ * the caller zeroes; the estimate is *sum_out / n.  RWMPT_ENOTSUP for families without such a sampler
+ * (FullRosenbrock -- the reference raises there too --, HybridRosenbrock, NealFunnel, Hypercube, IIDGamma, IIDBeta). */
+int rwmpt_swap_prob_estimate(const rwmpt_target_t* target, float beta_curr, float beta_star, int64_t n, uint64_t seed,
+                             int64_t row_id_base, double* sum_out, void* cuda_stream);
+
 /* Proposal increments, replaces ProposalDistribution.sample(n) (proposal_distributions/base.py:31-41):
  * out[n, dim]; row r uses Philox subsequence row_id_base + r. scale / dim_scale as in rwmpt_run_args_t
  * (scale is a single host float here). */

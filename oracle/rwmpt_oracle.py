@@ -508,3 +508,90 @@ def rough_carpet_density_cpu(x, modes=(-15.0, 0.0, 15.0), weights=(0.5, 0.3, 0.2
     for m, w in zip(modes, weights):
         dens = dens + w * np.exp(-0.5 * (x - m) ** 2) * c
     return float(np.prod(dens))
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# Iterative temperature-ladder construction
+# -------------------------------------------------------------------------------------------------------------------
+def tempered_samples_dim(spec: Dict, d: int, n: int, beta: float, rs: np.random.RandomState) -> np.ndarray:
+    """The targets' heuristic tempered samplers `draw_samples_torch(n, beta)`:
+    RoughCarpet multimodal_torch.py:532-565 (mode per coordinate ~ weights, (m + z / sqrt(beta)) / s);
+    ThreeMixture :270-333 (component per row, (mu_k + z / sqrt(beta)) / s); EvenRosenbrock rosenbrock_torch.py:224-248
+    (x_{2j} ~ N(mu_j, 1 / (2 a beta)), x_{2j+1} | x_{2j} ~ N(x_{2j}^2, 1 / (2 b beta))); ScaledMVN
+    multivariate_normal_torch.py:249-268; diagonal MVN :101-121."""
+    fam = spec["family"]
+    isb = F32(1.0) / np.sqrt(F32(beta))
+    z = rs.standard_normal((n, d)).astype(np.float32)
+    if fam == "rough_carpet":
+        w = np.exp(_f(spec["log_weights"]).astype(np.float64)); w = w / w.sum()
+        idx = rs.choice(3, size=(n, d), p=w)
+        y = _f(spec["modes"])[idx] + z * isb
+        return (y / _f(spec["scaling"])[None, :]).astype(np.float32) if "scaling" in spec else y.astype(np.float32)
+    if fam == "three_mixture":
+        w = np.exp(_f(spec["log_weights"]).astype(np.float64)); w = w / w.sum()
+        idx = rs.choice(3, size=n, p=w)
+        y = _f(spec["means"])[idx] + z * isb
+        return (y / _f(spec["scaling"])[None, :]).astype(np.float32) if "scaling" in spec else y.astype(np.float32)
+    if fam == "even_rosenbrock":
+        a, b = float(spec["a"]) * beta, float(spec["b"]) * beta
+        sa = np.sqrt(F32(1.0 / (2 * a))) if a > 0 else F32(1.0)
+        sb = np.sqrt(F32(1.0 / (2 * b))) if b > 0 else F32(1.0)
+        x = np.zeros((n, d), np.float32)
+        x[:, 0::2] = _f(spec["mu"])[None, :] + z[:, 0::2] * sa
+        x[:, 1::2] = x[:, 0::2] ** 2 + z[:, 1::2] * sb
+        return x
+    if fam == "scaled_mvn":
+        return (z * isb / _f(spec["c"])[None, :]).astype(np.float32)
+    if fam == "mvn_diag":
+        return (_f(spec["mean"])[None, :] + z * isb / np.sqrt(_f(spec["prec"]))[None, :]).astype(np.float32)
+    raise NotImplementedError(fam)
+
+
+def swap_probability(spec: Dict, d: int, beta_curr: float, beta_star: float, n: int, rs: np.random.RandomState):
+    """The estimate inside `_construct_iterative_ladder` (algorithms/pt_rwm_gpu_optimized.py:356-368):
+    mean(exp(clamp_max((beta - beta*) (log pi(x*) - log pi(x)), 0))), x* ~ sampler(beta*), x ~ sampler(beta).
+    Returns (estimate, Monte-Carlo standard error)."""
+    xs = tempered_samples_dim(spec, d, n, beta_star, rs)
+    xc = tempered_samples_dim(spec, d, n, beta_curr, rs)
+    log_r = F32(beta_curr - beta_star) * (log_density(spec, xs) - log_density(spec, xc))
+    p = np.exp(np.minimum(log_r, F32(0.0))).astype(np.float64)
+    return float(p.mean()), float(p.std(ddof=1) / np.sqrt(n))
+
+
+def iterative_ladder(estimate, target_rate: float = 0.234, beta_min: float = 0.01, n_samples: int = 3000, tolerance: float = 0.005,
+                     initial_pn: float = 0.5, pn_update_power: float = -0.25, max_pn_steps: int = 100,
+                     pn_clamp=(-10.0, 10.0), fail_tol_factor: float = 3.0) -> list:
+    """`_construct_iterative_ladder` (algorithms/pt_rwm_gpu_optimized.py:283-426) with a pluggable estimator
+    `estimate(beta_curr, beta_star, n) -> float`: beta* = beta / (1 + exp(p_n)); p_n <- p_n + n^power (a - target) until
+    |a - target| <= tolerance; a rung is also accepted after max_pn_steps when within fail_tol_factor * tolerance; the
+    ladder is closed with beta_min."""
+    ladder, beta_curr = [1.0], 1.0
+    while True:
+        if beta_curr <= beta_min + 1e-6:
+            break
+        pn, n_upd, found = initial_pn, 1, False
+        last_star, last_prob, it = -1.0, -1.0, 0
+        for it in range(1, max_pn_steps + 1):
+            cpn = float(np.clip(pn, pn_clamp[0], pn_clamp[1]))
+            beta_star = beta_curr / (1.0 + np.exp(cpn))
+            last_star = beta_star
+            if beta_star < beta_min:
+                break
+            prob = estimate(beta_curr, beta_star, n_samples)
+            last_prob = prob
+            if abs(prob - target_rate) <= tolerance:
+                ladder.append(beta_star)
+                beta_curr, found = beta_star, True
+                break
+            pn = pn + (n_upd ** pn_update_power) * (prob - target_rate)
+            n_upd += 1
+        if not found:
+            if it == max_pn_steps and last_star >= beta_min and last_star != -1.0 and \
+                    abs(last_prob - target_rate) <= tolerance * fail_tol_factor:
+                ladder.append(last_star)
+                beta_curr = last_star
+            else:
+                break
+    if ladder[-1] > beta_min + 1e-5:
+        ladder.append(beta_min)
+    return ladder

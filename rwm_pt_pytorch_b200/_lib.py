@@ -69,6 +69,7 @@ def _declare(lib):
     lib.rwmpt_pick_geometry.argtypes = [C.POINTER(RunArgs), C.POINTER(i32), C.POINTER(i32)]
     lib.rwmpt_log_density.argtypes = [C.POINTER(TargetT), vp, i64, vp, i32, vp]
     lib.rwmpt_proposal_sample.argtypes = [i32, i32, C.c_float, vp, i64, u64, i64, vp, vp]
+    lib.rwmpt_swap_prob_estimate.argtypes = [C.POINTER(TargetT), C.c_float, C.c_float, i64, u64, i64, vp, vp]
     lib.rwmpt_pt_swap.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, u64, i64, i64, vp, vp, vp]
     lib.rwmpt_esjd_reduce.argtypes = [vp, i64, i64, i64, i64, i32, vp, vp, vp]
     lib.rwmpt_debug_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -78,7 +79,7 @@ def _declare(lib):
     lib.rwmpt_probe_issue.restype = C.c_int
     lib.rwmpt_run_host.argtypes = [C.POINTER(RunArgs), i32, C.POINTER(u64), C.POINTER(u64)]
     for name in ("rwmpt_rwm_run", "rwmpt_pt_run", "rwmpt_pick_lanes", "rwmpt_pick_geometry", "rwmpt_log_density", "rwmpt_proposal_sample",
-                 "rwmpt_pt_swap", "rwmpt_esjd_reduce", "rwmpt_debug_philox", "rwmpt_run_host"):
+                 "rwmpt_pt_swap", "rwmpt_esjd_reduce", "rwmpt_debug_philox", "rwmpt_run_host", "rwmpt_swap_prob_estimate"):
         getattr(lib, name).restype = C.c_int
 
 
@@ -141,4 +142,5 @@ def exported_symbols():
     """Names declared in include/rwmpt.h (used by the CPU test that checks the library exports them all)."""
     return ["rwmpt_version", "rwmpt_last_error", "rwmpt_sizeof_run_args", "rwmpt_rwm_run", "rwmpt_pt_run",
             "rwmpt_count_swap_rounds", "rwmpt_pick_lanes", "rwmpt_pick_geometry", "rwmpt_log_density", "rwmpt_proposal_sample",
-            "rwmpt_pt_swap", "rwmpt_esjd_reduce", "rwmpt_probe_peaks", "rwmpt_probe_issue", "rwmpt_debug_philox", "rwmpt_run_host"]
+            "rwmpt_pt_swap", "rwmpt_esjd_reduce", "rwmpt_probe_peaks", "rwmpt_probe_issue", "rwmpt_debug_philox", "rwmpt_run_host",
+            "rwmpt_swap_prob_estimate"]

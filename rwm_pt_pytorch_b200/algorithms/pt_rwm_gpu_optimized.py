@@ -174,9 +174,31 @@ class ParallelTemperingRWM_GPU_Optimized(MHAlgorithm):
                                       "for iterative temperature ladder construction.")
         return self.target_dist.draw_samples_torch(N_samples, beta_val)
 
+    # families whose heuristic tempered sampler exists natively (csrc/rwmpt_ladder.cuh, Tempered<...>)
+    _NATIVE_LADDER_FAMILIES = (_lib.T_ROUGH_CARPET, _lib.T_THREE_MIXTURE, _lib.T_EVEN_ROSENBROCK, _lib.T_SCALED_MVN, _lib.T_MVN_DIAG)
+
     def _estimate_swap_probability(self, beta_curr: float, beta_star: float, n: int) -> float:
-        """mean(min(1, exp((beta - beta*) (log pi(x*) - log pi(x))))) over heuristic tempered samples (:356-368);
-        both log-densities come from the CUDA functor."""
+        """mean(min(1, exp((beta - beta*) (log pi(x*) - log pi(x))))) over heuristic tempered samples (:356-368).
+
+        Native path (`rwmpt_swap_prob_estimate`): ONE kernel draws both sample sets with in-kernel Philox, evaluates both
+        log-densities with the sampling kernel's functors and reduces to one fp64 -- nothing but the scalar leaves the
+        GPU, and reading it is the only synchronisation of a Robbins-Monro step.  Families without a native tempered
+        sampler use the target's `draw_samples_torch` with the CUDA log-density."""
+        t = self.target_dist
+        if getattr(t, "family_id", None) in self._NATIVE_LADDER_FAMILIES and self.device.type == "cuda" and torch.cuda.is_available():
+            dev = _lib.require_cuda(self.device)
+            lib = _lib.load()
+            if getattr(self, "_ladder_seed", None) is None:
+                from ..proposal_distributions.base import draw_seed
+                self._ladder_seed, self._ladder_rows = draw_seed(None), 0
+            params = t.device_params(dev)
+            acc = torch.zeros(1, dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.rwmpt_swap_prob_estimate(_lib.target_struct(t.family_id, self.dim, params), float(beta_curr),
+                                                        float(beta_star), int(n), self._ladder_seed, self._ladder_rows,
+                                                        acc.data_ptr(), _lib.stream_ptr(dev)))
+            self._ladder_rows += int(n)
+            return float(acc.item()) / int(n)
         xs = self._get_typical_samples_at_beta(beta_star, n)
         xc = self._get_typical_samples_at_beta(beta_curr, n)
         lps, lpc = self.target_dist.log_density(xs), self.target_dist.log_density(xc)

@@ -14,6 +14,19 @@ namespace rwmpt {
 
 static thread_local char g_err[512] = "";
 
+// family name (RWMPT_FAMILY_LIST) -> enum of include/rwmpt.h
+#define RWMPT_FAMILY_ID_rough_carpet RWMPT_T_ROUGH_CARPET
+#define RWMPT_FAMILY_ID_three_mixture RWMPT_T_THREE_MIXTURE
+#define RWMPT_FAMILY_ID_full_rosenbrock RWMPT_T_FULL_ROSENBROCK
+#define RWMPT_FAMILY_ID_even_rosenbrock RWMPT_T_EVEN_ROSENBROCK
+#define RWMPT_FAMILY_ID_hybrid_rosenbrock RWMPT_T_HYBRID_ROSENBROCK
+#define RWMPT_FAMILY_ID_neal_funnel RWMPT_T_NEAL_FUNNEL
+#define RWMPT_FAMILY_ID_hypercube RWMPT_T_HYPERCUBE
+#define RWMPT_FAMILY_ID_iid_gamma RWMPT_T_IID_GAMMA
+#define RWMPT_FAMILY_ID_iid_beta RWMPT_T_IID_BETA
+#define RWMPT_FAMILY_ID_scaled_mvn RWMPT_T_SCALED_MVN
+#define RWMPT_FAMILY_ID_mvn_diag RWMPT_T_MVN_DIAG
+
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -67,7 +80,8 @@ static int check_target(const rwmpt_target_t* t) {
 // Choose lanes-per-chain W and elements-per-lane E.  Candidates: E from the compiled list, W a power of two,
 // E*W >= d, no lane entirely padding, and the ladder (K*W threads) must fit one CTA.  Prefer the least padding;
 // among equals prefer more lanes while the grid is too small to fill the machine (latency hiding), else fewer.
-static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_W, LaunchGeom* g, int family = -1, int pf = -1) {
+static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_W, LaunchGeom* g, int family = -1, int pf = -1,
+                         bool for_mcmc = false) {
   const int* list = ieee ? kIeeeE : kFastE;
   const int n_list = ieee ? (int)(sizeof(kIeeeE) / sizeof(int)) : (int)(sizeof(kFastE) / sizeof(int));
   const long long n_chains = n_ladders * K;
@@ -96,6 +110,20 @@ static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_
       d > 49 && d <= 56 && K * 8 <= kMaxCtaThreads) {
     bestE = 7;
     bestW = 8;
+  }
+  g->variant = 0;
+  if (!ieee && for_mcmc) {
+    // tuning knobs for A/B measurements (results never depend on the geometry): RWMPT_GEOM="E,W" forces a tuned
+    // (elements per lane, lanes per chain) pair that a family's translation unit instantiates; RWMPT_VARIANT the loop variant
+    const char* eg = getenv("RWMPT_GEOM");
+    int fe = 0, fw = 0;
+    if (eg && sscanf(eg, "%d,%d", &fe, &fw) == 2 && fe >= 1 && fw >= 1 && fw <= 32 && (fw & (fw - 1)) == 0 &&
+        (long long)fe * fw >= d && (long long)K * fw <= kMaxCtaThreads) {
+      bestE = fe;
+      bestW = fw;
+    }
+    const char* ev = getenv("RWMPT_VARIANT");
+    if (ev) g->variant = atoi(ev);
   }
   if (bestE < 0)
     return fail(RWMPT_ENOTSUP, "no kernel variant for dim=%d n_temps=%d lanes_per_chain=%d (max dim %d; n_temps*lanes <= %d)",
@@ -155,6 +183,17 @@ static cudaError_t dispatch_logp(int family, const float* P, int d, int E, int W
   return cudaErrorInvalidValue;
 }
 
+static cudaError_t dispatch_swap_prob(int family, const float* P, int d, int E, int W, float bc, float bs, long long n, unsigned k0,
+                                      unsigned k1, long long row_base, double* sum_out, cudaStream_t st) {
+  switch (family) {
+#define X(name, cls) \
+  case RWMPT_FAMILY_ID_##name: return launch_swap_prob_##name(P, d, E, W, bc, bs, n, k0, k1, row_base, sum_out, st);
+    RWMPT_FAMILY_LIST(X)
+#undef X
+  }
+  return cudaErrorInvalidValue;
+}
+
 static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   if (!r) return fail(RWMPT_EINVAL, "args is NULL");
   int rc = check_target(&r->target);
@@ -192,7 +231,7 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
 
   LaunchGeom g;
   const bool ieee = r->math_mode == RWMPT_MATH_IEEE;
-  rc = pick_geometry(d, r->n_temps, r->n_ladders, ieee, r->lanes_per_chain, &g, r->target.family, r->proposal_family);
+  rc = pick_geometry(d, r->n_temps, r->n_ladders, ieee, r->lanes_per_chain, &g, r->target.family, r->proposal_family, true);
   if (rc) return rc;
   if (g.grid > 2147483647LL) return fail(RWMPT_ENOTSUP, "too many CTAs (%lld)", g.grid);
   if (r->schedule < RWMPT_SCHEDULE_AUTO || r->schedule > RWMPT_SCHEDULE_BALANCED)
@@ -522,7 +561,7 @@ int rwmpt_pick_geometry(const rwmpt_run_args_t* r, int32_t* lanes_per_chain, int
   if (r->target.dim < 1 || r->n_temps < 1 || r->n_ladders < 1) return fail(RWMPT_EINVAL, "dim, n_temps, n_ladders must be >= 1");
   LaunchGeom g;
   const int rc = pick_geometry(r->target.dim, r->n_temps, r->n_ladders, r->math_mode == RWMPT_MATH_IEEE, r->lanes_per_chain, &g,
-                               r->target.family, r->proposal_family);
+                               r->target.family, r->proposal_family, true);
   if (rc) return rc;
   if (lanes_per_chain) *lanes_per_chain = g.W;
   if (elems_per_lane) *elems_per_lane = g.E;
@@ -542,6 +581,29 @@ int rwmpt_log_density(const rwmpt_target_t* target, const float* x, int64_t n, f
   if (rc) return rc;
   cudaError_t e = dispatch_logp(target->family, target->params, target->dim, g.E, g.W, x, n, out, ieee, (cudaStream_t)cuda_stream);
   if (e != cudaSuccess) return cuda_fail(e, "log-density kernel launch");
+  return RWMPT_OK;
+}
+
+int rwmpt_swap_prob_estimate(const rwmpt_target_t* target, float beta_curr, float beta_star, int64_t n, uint64_t seed,
+                             int64_t row_id_base, double* sum_out, void* cuda_stream) {
+  int rc = check_target(target);
+  if (rc) return rc;
+  if (n < 0) return fail(RWMPT_EINVAL, "n must be >= 0");
+  if (!(beta_curr > 0.0f) || !(beta_star > 0.0f)) return fail(RWMPT_EINVAL, "beta_curr and beta_star must be positive");
+  if (!sum_out) return fail(RWMPT_EINVAL, "sum_out is NULL");
+  if (n == 0) return RWMPT_OK;
+  LaunchGeom g;
+  rc = pick_geometry(target->dim, 1, n, false, 0, &g);
+  if (rc) return rc;
+  cudaError_t e = dispatch_swap_prob(target->family, target->params, target->dim, g.E, g.W, beta_curr, beta_star, n,
+                                     (unsigned)(seed & 0xffffffffu), (unsigned)(seed >> 32), row_id_base, sum_out,
+                                     (cudaStream_t)cuda_stream);
+  if (e == cudaErrorNotSupported) {
+    cudaGetLastError();
+    return fail(RWMPT_ENOTSUP, "target family %d has no native tempered sampler (use draw_samples_torch + rwmpt_log_density)",
+                target->family);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "swap-probability kernel launch");
   return RWMPT_OK;
 }
 

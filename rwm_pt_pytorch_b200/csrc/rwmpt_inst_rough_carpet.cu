@@ -3,6 +3,7 @@
 #include "rwmpt_launch.cuh"
 #define TUNED_LIST(cls)                                               \
   RWMPT_TUNED_PLAIN_CASE(cls, rwmpt::RoughCarpetPlain, 5, 4, 0)       \
+  RWMPT_TUNED_PLAIN_CASE(cls, rwmpt::RoughCarpetPlain, 10, 2, 0)      \
   RWMPT_TUNED_CASE(cls, 5, 4, 0)
 RWMPT_DEFINE_TUNED(rwmpt::RoughCarpet, TUNED_LIST)
 RWMPT_DEFINE_FAMILY(rough_carpet, RoughCarpet)

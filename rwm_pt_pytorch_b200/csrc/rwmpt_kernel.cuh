@@ -305,10 +305,19 @@ __device__ __forceinline__ bool swap_accept(float bj, float bk, float lj, float 
 // One unit of work: the chains of CTA index `cta` (whole ladders) advanced by `n_steps` steps from global step
 // `step_offset`.  SLICED: the unit is one time slice of a balanced launch -- another CTA (possibly on another SM) ran
 // the previous slice, so state is read past L1 and the accumulators are updated with atomics.
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool SLICED, bool STORE>
+//
+// LEAN: two-stage loop for workloads with MANY chains per SM (BASELINE config 5: 16 384 chains of d = 100).  The three-stage
+// pipeline below keeps the words of pair p+2, the increments of pair p+1 and the increments of pair p live at once
+// (~250 registers at E = 13: two warps per scheduler); the lean loop draws and transforms the words of pair p+1 right
+// after the steps of pair p, in place, and is compiled under a register cap so that more warps are resident -- thread
+// level parallelism instead of instruction level parallelism.  Same words, same increments, same results.
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool SLICED, bool STORE, int LEANMODE = 0>
 __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long cta, const long long step_offset,
                                           const long long n_steps, const long long rounds_before) {
   using M = Mth<IEEE>;
+  // LEANMODE 1: lean loop, words from PhiloxPairGen (4 registers of run-invariant round state per Philox call);
+  // LEANMODE 2: lean loop, ten plain rounds per call (no invariant registers: the leanest form)
+  constexpr bool LEAN = LEANMODE != 0;
   extern __shared__ __align__(16) float smem[];  // staged rows are flushed as float4 / float2 vectors
 
   const int W = WT > 0 ? WT : a.W;
@@ -702,12 +711,15 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
         // earlier) are turned into increments and the words of pair p+2 are drawn -- three instruction streams with no
         // dependencies between them inside one iteration.
         constexpr int NCW = PairWords<E, PF>::NC;
+        constexpr unsigned DD = LEAN ? 1u : 2u;  // how many pairs ahead of the pair being stepped the words are drawn
         uint32_t wn[4 * NCW];
         auto ensure_gen = [&](unsigned long long p) {
           if ((uint32_t)(p >> 32) != gen.hi32) gen.init(a.rk, c.sub, p, chain_gid);
         };
-        ensure_gen(pair + 1);
-        gen.gen(a.rk, (uint32_t)(pair + 1), wn);
+        if constexpr (!LEAN) {
+          ensure_gen(pair + 1);
+          gen.gen(a.rk, (uint32_t)(pair + 1), wn);
+        }
         // The loop runs in chunks that end where something other than a plain pair is due: a sweep after the chunk's last
         // step, the accumulator flush (every chunk end), a change of the high word of the Philox pair counter, or the end
         // of the fast run.
@@ -721,16 +733,28 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
         auto chunk_len = [&]() -> int {
           int m = left32 < RWMPT_CHUNK ? left32 : RWMPT_CHUNK;
           m = m < sw ? m : sw;
-          const uint32_t room = 0u - (plo + 2u);   // draws before the low word of the Philox counter wraps (0: a full 2^32)
+          const uint32_t room = 0u - (plo + DD);   // draws before the low word of the Philox counter wraps (0: a full 2^32)
           if (room != 0u && (uint32_t)m > room) m = (int)room;
           return m;
         };
-        ensure_gen(pair + 2);
+        ensure_gen(pair + DD);
         int len = chunk_len();
         plo_end = plo + (uint32_t)len;
         for (;;) {
           float nA[E], nB[E], vA, vB, xo[E], jadd;
           uint32_t tA, tB;
+          if constexpr (LEAN) {
+            plain_step(iA, uA, store_tag, xo, jadd, jf, cnt);
+            plain_step(iB, uB, std::false_type{}, xo, jadd, jf, cnt);
+            if constexpr (LEANMODE == 2) {
+              PairWords<E, PF> pw;
+              pw.full(a.rk, c.sub, pair + (unsigned long long)(uint32_t)(plo - (uint32_t)pair) + 1ull, chain_gid);
+              pair_transform<E, IEEE, PF>(a, c, pw.w, nA, nB, vA, vB, tA, tB, scale, dscale);
+            } else {
+              gen.gen(a.rk, plo + 1u, wn);
+              pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, tA, tB, scale, dscale);
+            }
+          } else {
 #if RWMPT_ORDER == 1
           pair_transform<E, IEEE, PF>(a, c, wn, nA, nB, vA, vB, tA, tB, scale, dscale);
           gen.gen(a.rk, plo + 2u, wn);
@@ -752,6 +776,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
           gen.gen(a.rk, plo + 2u, wn);
           plain_step(iB, uB, std::false_type{}, xo, jadd, jf, cnt);
 #endif
+          }
           ++plo;
 #pragma unroll
           for (int e = 0; e < E; ++e) { iA[e] = nA[e]; iB[e] = nB[e]; }
@@ -777,7 +802,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
             jf = 0.0f; cnt = 0;
             done = left32 == 0;
             if (!done) {
-              if (plo + 2u < 2u) ensure_gen(pair + 2);  // the low word of the next draw wrapped
+              if (plo + DD < DD) ensure_gen(pair + DD);  // the low word of the next draw wrapped
               len = chunk_len();
               plo_end = plo + (uint32_t)len;
             }
@@ -861,8 +886,17 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
 // publish.  A ladder is always being advanced by exactly one CTA, the spare CTAs sleep, and the time a warp spends
 // alone on its scheduler (where it runs ~1.7x faster) is shared by all ladders instead of ending in an idle tail.
 // Results do not depend on the schedule: a slice resumes exactly like a host-level resume (step_offset).
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE>
-__global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a) {
+//
+// VARIANT (tuned instantiations only): 0 = three-stage pipeline, any CTA size; 1 / 2 = lean loop for one-warp CTAs compiled
+// for >= 16 / >= 12 resident CTAs per SM (<= 128 / <= 168 registers: 4 / 3 warps per scheduler); 3 / 4 = the same with ten
+// plain Philox rounds per call instead of the PhiloxPairGen invariants (fewer live registers).
+__host__ __device__ constexpr int variant_threads(int v) { return v == 0 ? kMaxCtaThreads : 32; }
+__host__ __device__ constexpr int variant_min_ctas(int v) { return (v == 1 || v == 3) ? 16 : ((v == 2 || v == 4) ? 12 : 1); }
+__host__ __device__ constexpr int variant_leanmode(int v) { return v == 0 ? 0 : (v <= 2 ? 1 : 2); }
+
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE, int VARIANT = 0>
+__global__ void __launch_bounds__(variant_threads(VARIANT), variant_min_ctas(VARIANT)) mcmc_kernel(const KernelArgs a) {
+  constexpr int LEAN = variant_leanmode(VARIANT);
   if constexpr (TEST) {
     mcmc_unit<Target, E, IEEE, WT, PF, EXACT, TEST, false, STORE>(a, (long long)blockIdx.x, a.step_offset, a.n_steps, a.rounds_before);
   } else {
@@ -900,7 +934,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads) mcmc_kernel(const KernelArgs a
         rb = (a.K > 1 && so > a.burn_in) ? so / a.swap_every - a.burn_in / a.swap_every : 0;
       }
       // (L1-bypassing loads and atomic accumulators of the sliced unit are harmless in a plain launch)
-      mcmc_unit<Target, E, IEEE, WT, PF, EXACT, TEST, true, STORE>(a, unit, so, n, rb);
+      mcmc_unit<Target, E, IEEE, WT, PF, EXACT, TEST, true, STORE, LEAN>(a, unit, so, n, rb);
       if (!sliced) break;
       __threadfence();
       __syncthreads();
@@ -954,6 +988,7 @@ struct LaunchGeom {
   size_t smem;
   int sms;       // SM count of the current device
   int schedule;  // RWMPT_SCHEDULE_*
+  int variant;   // tuned kernels: loop variant (see mcmc_kernel); 0 unless the geometry table or RWMPT_VARIANT says otherwise
 };
 
 }  // namespace rwmpt

@@ -15,7 +15,7 @@ namespace rwmpt {
 #define RWMPT_IEEE_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
 #endif
 
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE>
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE, int VARIANT = 0>
 cudaError_t launch_mcmc_store(const KernelArgs& a_in, const LaunchGeom& g, cudaStream_t st);
 
 // Fast (non-test) kernels exist twice: with and without the retained-sample path, so that the accumulators-only kernels
@@ -35,9 +35,13 @@ struct SplitStore<RoughCarpetPlain> {
   static constexpr bool value = false;
 };
 
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST>
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, int VARIANT = 0>
 cudaError_t launch_mcmc_one(const KernelArgs& a_in, const LaunchGeom& g, cudaStream_t st) {
-  if constexpr (TEST || !SplitStore<Target>::value) {
+  if constexpr (VARIANT != 0) {
+    // lean variants: accumulators-only runs of one-warp CTAs; anything else takes the pipelined kernel of the same geometry
+    if (a_in.samples != nullptr || g.threads != 32) return launch_mcmc_one<Target, E, IEEE, WT, PF, EXACT, TEST, 0>(a_in, g, st);
+    return launch_mcmc_store<Target, E, IEEE, WT, PF, EXACT, TEST, false, VARIANT>(a_in, g, st);
+  } else if constexpr (TEST || !SplitStore<Target>::value) {
     return launch_mcmc_store<Target, E, IEEE, WT, PF, EXACT, TEST, true>(a_in, g, st);
   } else {
     if (a_in.samples != nullptr) return launch_mcmc_store<Target, E, IEEE, WT, PF, EXACT, TEST, true>(a_in, g, st);
@@ -45,9 +49,9 @@ cudaError_t launch_mcmc_one(const KernelArgs& a_in, const LaunchGeom& g, cudaStr
   }
 }
 
-template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE>
+template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE, int VARIANT>
 cudaError_t launch_mcmc_store(const KernelArgs& a_in, const LaunchGeom& g, cudaStream_t st) {
-  auto kern = mcmc_kernel<Target, E, IEEE, WT, PF, EXACT, TEST, STORE>;
+  auto kern = mcmc_kernel<Target, E, IEEE, WT, PF, EXACT, TEST, STORE, VARIANT>;
   if (g.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
@@ -157,7 +161,11 @@ cudaError_t launch_logp_family(const float* P, int d, int E, int W, const float*
   return cudaErrorInvalidValue;
 }
 
-// one pair of entry points per family, defined in rwmpt_inst_<family>.cu
+}  // namespace rwmpt
+#include "rwmpt_ladder.cuh"
+namespace rwmpt {
+
+// one set of entry points per family, defined in rwmpt_inst_<family>.cu
 #define RWMPT_FAMILY_LIST(X)                 \
   X(rough_carpet, RoughCarpet)               \
   X(three_mixture, ThreeMixture)             \
@@ -174,7 +182,9 @@ cudaError_t launch_logp_family(const float* P, int d, int E, int W, const float*
 #define X(name, cls)                                                                                         \
   cudaError_t launch_mcmc_##name(const KernelArgs& a, const LaunchGeom& g, bool ieee, cudaStream_t st);       \
   cudaError_t launch_logp_##name(const float* P, int d, int E, int W, const float* x, long long n, float* out, \
-                                 bool ieee, cudaStream_t st);
+                                 bool ieee, cudaStream_t st);                                                 \
+  cudaError_t launch_swap_prob_##name(const float* P, int d, int E, int W, float bc, float bs, long long n,     \
+                                      unsigned k0, unsigned k1, long long row_base, double* sum_out, cudaStream_t st);
 RWMPT_FAMILY_LIST(X)
 #undef X
 
@@ -183,6 +193,12 @@ RWMPT_FAMILY_LIST(X)
   if (g.E == e && g.W == w && a.prop_family == pf) {                              \
     if (a.dim == e * w) return launch_mcmc_one<cls, e, false, w, pf, true, false>(a, g, st);  \
     return launch_mcmc_one<cls, e, false, w, pf, false, false>(a, g, st);                     \
+  }
+// lean-loop variant v (1 or 2, see mcmc_kernel) of a tuned case; list it BEFORE the pipelined case of the same geometry
+#define RWMPT_TUNED_CASE_V(cls, e, w, pf, v)                                                         \
+  if (g.variant == v && g.E == e && g.W == w && a.prop_family == pf) {                              \
+    if (a.dim == e * w) return launch_mcmc_one<cls, e, false, w, pf, true, false, v>(a, g, st);     \
+    return launch_mcmc_one<cls, e, false, w, pf, false, false, v>(a, g, st);                        \
   }
 // tuned case that swaps in a leaner functor (e.g. RoughCarpetPlain) when the target carries no scaling block
 #define RWMPT_TUNED_PLAIN_CASE(cls, plain, e, w, pf)                                               \
@@ -209,6 +225,11 @@ RWMPT_FAMILY_LIST(X)
   cudaError_t launch_logp_##name(const float* P, int d, int E, int W, const float* x, long long n, float* out, \
                                  bool ieee, cudaStream_t st) {                                                \
     return launch_logp_family<cls>(P, d, E, W, x, n, out, ieee, st);                                          \
+  }                                                                                                           \
+  cudaError_t launch_swap_prob_##name(const float* P, int d, int E, int W, float bc, float bs, long long n,    \
+                                      unsigned k0, unsigned k1, long long row_base, double* sum_out,          \
+                                      cudaStream_t st) {                                                      \
+    return launch_swap_prob_family<cls>(P, d, E, W, bc, bs, n, k0, k1, row_base, sum_out, st);                \
   }                                                                                                           \
   }
 

@@ -20,11 +20,15 @@ from .algorithms import RandomWalkMH_GPU_Optimized, ParallelTemperingRWM_GPU_Opt
 from .proposal_distributions import NormalProposal, LaplaceProposal, UniformRadiusProposal
 
 
-def get_target_distribution(name: str, dim: int, device=None, **kwargs):
-    """Target factory with the experiment defaults of the reference (experiment_RWM_GPU.py:21-117)."""
+def get_target_distribution(name: str, dim: int, device=None, pt: bool = False, **kwargs):
+    """Target factory with the experiment defaults of the reference: experiment_RWM_GPU.py:21-117 (RoughCarpet modes +-4,
+    ThreeMixture centres +-5) or, with pt=True, experiment_pt_GPU.py:21-117 (modes / centres +-15)."""
     if device is None:
         device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
-    three_centers = [[-5.0] + [0.0] * (dim - 1), [0.0] * dim, [5.0] + [0.0] * (dim - 1)]
+    sep = 15.0 if pt else 5.0
+    three_centers = [[-sep] + [0.0] * (dim - 1), [0.0] * dim, [sep] + [0.0] * (dim - 1)]
+    if pt:
+        kwargs.setdefault('mode_centers', three_centers if name.startswith("ThreeMixture") else [-15.0, 0.0, 15.0])
     if name == "MultivariateNormal":
         return td.MultivariateNormalTorch(dim, device=device)
     if name == "MultivariateNormalScaled":
@@ -123,7 +127,7 @@ def run_pt_study(dim, target_name="ThreeMixture", num_iters=100000, swap_accept_
                  out_dir: Optional[str] = None, device=None, **kwargs) -> dict:
     """PT-ESJD versus target swap rate (experiment_pt_GPU.py:165-279): each of the `num_values` rates in
     linspace(0.01, swap_accept_max) builds its iterative ladder and runs `ladders_per_value` ladders in one launch."""
-    target = get_target_distribution(target_name, dim, device=device or "cuda", **kwargs)
+    target = get_target_distribution(target_name, dim, device=device or "cuda", pt=True, **kwargs)
     d = target.dim
     rates = np.linspace(0.01, swap_accept_max, num_values)
     var = (2.38 ** 2) / d

@@ -318,6 +318,41 @@ def gen_numpy_c1(n_steps=4000):
          esjd=float(np.mean(np.sum((chain[1:] - chain[:-1]) ** 2, axis=1))))
 
 
+# --- iterative temperature ladder: the reference's own ladder and its swap-probability estimator --------
+def gen_ladder(name, target, target_rate, n_est, seed):
+    """ladder_*.npz: (i) the ladder `_construct_iterative_ladder` (pt_rwm_gpu_optimized.py:283-426) builds on the torch CPU
+    device, with the estimate it accepted for every rung; (ii) the reference's estimator itself -- draw_samples_torch at both
+    temperatures, log_density, mean(exp(clamp_max(.,0))) (:356-368) -- on a grid of (beta, beta*) pairs with 4e5 samples
+    each, with its Monte-Carlo standard error.  The CUDA estimator is checked against (ii) pair by pair and must rebuild
+    (i) rung by rung."""
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        algo = ref_pt_mod.ParallelTemperingRWM_GPU_Optimized(
+            dim=target.dim, var=2.38 ** 2 / target.dim, target_dist=target, iterative_temp_spacing=True,
+            swap_acceptance_rate=target_rate, N_samples_swap_est=n_est, swap_every=10, device="cpu", pre_allocate_steps=10)
+    ladder = np.asarray(algo.beta_ladder, dtype=np.float64)
+    betas, stars, est, se = [], [], [], []
+    g = torch.Generator().manual_seed(seed + 1)
+    pairs = [(float(ladder[k]), float(ladder[k + 1])) for k in range(len(ladder) - 1)]
+    for b in (1.0, 0.3, 0.05):                       # off-ladder pairs: ratios from near-certain to rare swaps
+        for ratio in (0.95, 0.8, 0.5):
+            pairs.append((b, b * ratio))
+    N = 400_000
+    for bc, bs in pairs:
+        torch.manual_seed(int(torch.randint(0, 2 ** 31, (1,), generator=g)))
+        xs = target.draw_samples_torch(N, bs)
+        xc = target.draw_samples_torch(N, bc)
+        log_r = (bc - bs) * (target.log_density(xs) - target.log_density(xc))
+        p = torch.exp(torch.clamp_max(log_r, 0.0)).double()
+        betas.append(bc); stars.append(bs); est.append(float(p.mean())); se.append(float(p.std() / np.sqrt(N)))
+    save(name, spec_of(target), ladder=ladder, target_rate=target_rate, n_est=n_est, tolerance=0.005,
+         pair_beta=np.asarray(betas), pair_beta_star=np.asarray(stars), pair_estimate=np.asarray(est), pair_se=np.asarray(se),
+         n_ladder_pairs=len(ladder) - 1, dim=target.dim)
+    print(f"  {name}: {len(ladder)} rungs", np.round(ladder, 5).tolist())
+
+
 def main():
     T = make_targets()
     for name, t in T.items():
@@ -369,6 +404,12 @@ def main():
            beta_ladder=[float(b) for b in np.geomspace(1.0, 0.01, 13)])
     gen_pt("pt_iid_gamma_d8_k2", T["iid_gamma_d8"], 300, 0, seed=6, var=1.0, swap_every=2, beta_ladder=[1.0, 0.3])
     gen_numpy_c1()
+    # ladder_*: built last so that the fixtures above keep their RNG streams
+    gen_ladder("ladder_rough_carpet_pm15_d20", td.RoughCarpetDistributionTorch(20, device=CPU, mode_centers=[-15.0, 0.0, 15.0]),
+               0.234, 20000, seed=31)
+    gen_ladder("ladder_three_mixture_pm15_d30", td.ThreeMixtureDistributionTorch(
+        30, device=CPU, mode_centers=[[-15.0] + [0.0] * 29, [0.0] * 30, [15.0] + [0.0] * 29], mode_weights=[1 / 3, 1 / 3, 1 / 3]),
+        0.234, 20000, seed=32)
 
 
 if __name__ == "__main__":

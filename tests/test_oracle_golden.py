@@ -119,3 +119,31 @@ def test_numpy_cpu_sampler_restatement():
     np.testing.assert_allclose(out["chain"][-2:], g["chain_tail"], rtol=1e-9, atol=1e-12)
     assert out["acceptance_rate"] == pytest.approx(float(g["acceptance_rate"]), rel=1e-12)
     assert out["esjd"] == pytest.approx(float(g["esjd"]), rel=1e-9)
+
+
+@pytest.mark.parametrize("name", golden_names("ladder_"))
+def test_swap_probability_estimator_and_ladder_match_reference(name):
+    """The oracle's restatement of the iterative-ladder estimator (pt_rwm_gpu_optimized.py:356-368 + the targets'
+    draw_samples_torch) against the reference's own estimates on a grid of (beta, beta*) pairs, and the ladder the
+    restated recursion (:283-426) builds against the reference's ladder, rung by rung."""
+    spec, g = load_golden(name)
+    d = int(g["dim"])
+    rs = np.random.RandomState(7)
+    N = 40_000
+    for bc, bs, ref, se in zip(g["pair_beta"], g["pair_beta_star"], g["pair_estimate"], g["pair_se"]):
+        est, se_o = O.swap_probability(spec, d, float(bc), float(bs), N, rs)
+        assert abs(est - ref) <= 4.5 * np.hypot(se, se_o) + 1e-4, (bc, bs, est, ref, se, se_o)
+    # every rung the reference accepted had an estimate within `tolerance` of the target (it used n_est samples): with the
+    # oracle's estimator at the reference's rungs the rate must be the target within tolerance + Monte-Carlo error
+    lad = g["ladder"]
+    k_pairs = int(g["n_ladder_pairs"])
+    for k in range(k_pairs - 1):            # the last rung is the forced beta_min
+        est, se_o = O.swap_probability(spec, d, float(lad[k]), float(lad[k + 1]), N, rs)
+        se_ref = np.sqrt(0.25 / float(g["n_est"]))      # the reference's own estimate: n_est samples, variance <= 1/4
+        assert abs(est - float(g["target_rate"])) <= float(g["tolerance"]) + 4 * np.hypot(se_o, se_ref), (k, est)
+    # the restated recursion rebuilds the ladder: same number of rungs (+-1), rungs within 12 % of the reference's
+    mine = O.iterative_ladder(lambda b, bs, n: O.swap_probability(spec, d, b, bs, n, rs)[0], target_rate=float(g["target_rate"]),
+                              n_samples=int(g["n_est"]))
+    assert abs(len(mine) - len(lad)) <= 1, (mine, lad.tolist())
+    m = min(len(mine), len(lad)) - 1
+    np.testing.assert_allclose(mine[:m], lad[:m], rtol=0.12)
