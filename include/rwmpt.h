@@ -52,7 +52,13 @@ enum {
   RWMPT_T_SCALED_MVN = 9,        /* multivariate_normal_torch.py:198-223  P[0] log norm const; P[16..16+d) c     */
   RWMPT_T_MVN_DIAG = 10,         /* multivariate_normal_torch.py:62-92 with diagonal cov: P[0] log norm const;
                                     P[16..16+d) mean, then d diagonal precisions                                 */
-  RWMPT_T_COUNT = 11
+  RWMPT_T_MVN_DENSE = 11,        /* multivariate_normal_torch.py:62-92 with a general covariance: P[0] log norm const;
+                                    P[16..16+d) mean, then cov_inv row-major (d x d); dim <= 128                  */
+  RWMPT_T_SUPER_FUNNEL = 12,     /* funnel_torch.py:193-291 (hierarchical logistic regression)  P[0] J, P[1] K,
+                                    P[2] prior hyper-mean var, P[3] its log, P[4] prior tau scale, P[5] its log,
+                                    P[6] log 2pi, P[7] log 2, P[8] log pi, P[9] N; then N records (group, y, x[K]);
+                                    dim = J + J K + K + 3 <= 128                                                 */
+  RWMPT_T_COUNT = 13
 };
 #define RWMPT_PARAM_HEADER 16
 

@@ -209,6 +209,58 @@ LOGP = {
 }
 
 
+def logp_mvn_dense(x, spec):
+    """`MultivariateNormalTorch.log_density` with a general covariance, multivariate_normal_torch.py:62-92:
+    temp = centered @ cov_inv; q = sum(temp * centered, dim=1); -0.5 q + log_norm_const (fp32; the matmul's summation
+    order is the BLAS's, so comparisons are to ~1e-5 relative)."""
+    cen = (x - _f(spec["mean"])[None, :]).astype(np.float32)
+    temp = (cen @ _f(spec["cov_inv"])).astype(np.float32)
+    q = np.sum(temp * cen, axis=1, dtype=np.float32)
+    return (F32(-0.5) * q + F32(spec["log_norm_const"])).astype(np.float32)
+
+
+def _log_sigmoid(z):
+    z = z.astype(np.float32)
+    return (np.minimum(z, F32(0.0)) - np.log1p(np.exp(-np.abs(z)))).astype(np.float32)
+
+
+def logp_super_funnel(x, spec):
+    """`SuperFunnelTorch.log_density`, funnel_torch.py:193-291: Bernoulli-logit likelihood over the N records
+    (group, y, x[K]), Normal priors on alpha_j / beta_jk around the hyper-means with scales tau_alpha / tau_beta, Normal
+    priors on the hyper-means, half-Cauchy priors on the taus; -inf when a tau is <= 1e-9."""
+    J, K = int(spec["J"]), int(spec["K"])
+    rec = _f(spec["records"])
+    B = x.shape[0]
+    al = x[:, :J]
+    be = x[:, J:J + J * K].reshape(B, J, K)
+    o = J + J * K
+    mu_a, mu_b, tau_a, tau_b = x[:, o], x[:, o + 1:o + 1 + K], x[:, o + 1 + K], x[:, o + 2 + K]
+    valid = (tau_a > 1e-9) & (tau_b > 1e-9)
+    g = rec[:, 0].astype(np.int64)
+    y = rec[:, 1][None, :]
+    eta = (al[:, g] + np.einsum('nk,bnk->bn', rec[:, 2:], be[:, g, :])).astype(np.float32)
+    ll = np.sum(y * _log_sigmoid(eta) + (F32(1.0) - y) * _log_sigmoid(-eta), axis=1, dtype=np.float32)
+    sa = np.where(valid, tau_a, F32(1.0)).astype(np.float32)
+    sb = np.where(valid, tau_b, F32(1.0)).astype(np.float32)
+    l2p = F32(spec["log_2pi"])
+    pa = np.sum(F32(-0.5) * l2p - np.log(sa)[:, None] - F32(0.5) * (al - mu_a[:, None]) ** 2 / (sa[:, None] ** 2), axis=1, dtype=np.float32)
+    sq = np.sum((be - mu_b[:, None, :]) ** 2, axis=2, dtype=np.float32)
+    pb = np.sum(F32(-0.5) * F32(K) * l2p - F32(K) * np.log(sb)[:, None] - F32(0.5) * sq / (sb[:, None] ** 2), axis=1, dtype=np.float32)
+    hv, lhv = F32(spec["hyper_var"]), F32(spec["log_hyper_var"])
+    p_ma = F32(-0.5) * l2p - F32(0.5) * lhv - F32(0.5) * mu_a ** 2 / hv
+    p_mb = F32(-0.5) * F32(K) * l2p - F32(0.5) * F32(K) * lhv - F32(0.5) * np.sum(mu_b ** 2, axis=1, dtype=np.float32) / hv
+    ts, lts = F32(spec["tau_scale"]), F32(spec["log_tau_scale"])
+    with np.errstate(invalid="ignore"):
+        p_ta = F32(spec["log_2"]) - F32(spec["log_pi"]) - lts - np.log1p((tau_a / ts) ** 2)
+        p_tb = F32(spec["log_2"]) - F32(spec["log_pi"]) - lts - np.log1p((tau_b / ts) ** 2)
+        out = (ll + pa + pb + p_ma + p_mb + p_ta + p_tb).astype(np.float32)
+    return np.where(valid, out, F32(-np.inf)).astype(np.float32)
+
+
+LOGP["mvn_dense"] = logp_mvn_dense
+LOGP["super_funnel"] = logp_super_funnel
+
+
 def log_density(spec: Dict, x) -> np.ndarray:
     """Dispatch on spec['family']; x is (d,) or (..., d)."""
     x = _f(x)

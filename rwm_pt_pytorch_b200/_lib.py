@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("RWMPT_LIB", os.path.join(_PKG, "librwmpt.so"))  # RWM
 # enums of include/rwmpt.h
 T_ROUGH_CARPET, T_THREE_MIXTURE, T_FULL_ROSENBROCK, T_EVEN_ROSENBROCK, T_HYBRID_ROSENBROCK = 0, 1, 2, 3, 4
 T_NEAL_FUNNEL, T_HYPERCUBE, T_IID_GAMMA, T_IID_BETA, T_SCALED_MVN, T_MVN_DIAG = 5, 6, 7, 8, 9, 10
+T_MVN_DENSE, T_SUPER_FUNNEL = 11, 12
 PARAM_HEADER = 16
 P_NORMAL, P_LAPLACE, P_UNIFORM_RADIUS = 0, 1, 2
 SWAP_REFERENCE, SWAP_EXCHANGE = 0, 1

@@ -26,6 +26,8 @@ static thread_local char g_err[512] = "";
 #define RWMPT_FAMILY_ID_iid_beta RWMPT_T_IID_BETA
 #define RWMPT_FAMILY_ID_scaled_mvn RWMPT_T_SCALED_MVN
 #define RWMPT_FAMILY_ID_mvn_diag RWMPT_T_MVN_DIAG
+#define RWMPT_FAMILY_ID_mvn_dense RWMPT_T_MVN_DENSE
+#define RWMPT_FAMILY_ID_super_funnel RWMPT_T_SUPER_FUNNEL
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -59,6 +61,7 @@ static int64_t min_params(int family, int d) {
     case RWMPT_T_EVEN_ROSENBROCK: return H + d / 2;
     case RWMPT_T_SCALED_MVN: return H + d;
     case RWMPT_T_MVN_DIAG: return H + 2LL * d;
+    case RWMPT_T_MVN_DENSE: return H + d + (int64_t)d * d;
     default: return H;
   }
 }
@@ -74,6 +77,8 @@ static int check_target(const rwmpt_target_t* t) {
   if (t->family == RWMPT_T_EVEN_ROSENBROCK && (t->dim < 2 || t->dim % 2))
     return fail(RWMPT_EINVAL, "EvenRosenbrock needs an even dim >= 2");
   if ((t->family == RWMPT_T_FULL_ROSENBROCK) && t->dim < 2) return fail(RWMPT_EINVAL, "FullRosenbrock needs dim >= 2");
+  if ((t->family == RWMPT_T_MVN_DENSE || t->family == RWMPT_T_SUPER_FUNNEL) && t->dim > kMaxGather)
+    return fail(RWMPT_ENOTSUP, "target family %d gathers the whole state on every lane: dim <= %d", t->family, kMaxGather);
   return RWMPT_OK;
 }
 
@@ -88,11 +93,15 @@ static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_
   const double fill_threads = 148.0 * 4 * 32 * 4;  // ~4 warps per scheduler
   double best_score = 1e300;
   int bestE = -1, bestW = -1;
+  // two passes: the register-friendly elements-per-lane counts first (E <= 13); E = 25 only when nothing else fits (a long
+  // ladder whose n_temps * lanes would exceed one CTA, or a dimension above 13 * 32)
+  for (int pass = 0; pass < 2 && bestE < 0; ++pass)
   for (int W = 1; W <= 32; W *= 2) {
     if (want_W > 0 && W != want_W) continue;
     if ((long long)K * W > kMaxCtaThreads) continue;
     for (int k = 0; k < n_list; ++k) {
       const int E = list[k];
+      if (pass == 0 && E > 13) break;
       if ((long long)E * W < d) continue;
       if (want_W <= 0 && W > 1 && (long long)(W - 1) * E >= d) continue;  // auto mode: no lane that is all padding
       const double waste = (double)E * W / d;
@@ -121,6 +130,13 @@ static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_
         (long long)fe * fw >= d && (long long)K * fw <= kMaxCtaThreads) {
       bestE = fe;
       bestW = fw;
+    }
+    // measured defaults (profiles/r2_variant_ab.txt): with thousands of one-warp units per GPU the lean loop under a register
+    // cap beats the three-stage pipeline -- BASELINE config 5, d = 100 on 13 x 8: FullRosenbrock +23 % with <= 128
+    // registers (4 warps per scheduler), NealFunnel +13 % with <= 168 (3 per scheduler)
+    if (bestE == 13 && bestW == 8 && pf == RWMPT_P_NORMAL && K == 1 && n_chains * bestW / 32 >= 148LL * 12) {
+      if (family == RWMPT_T_FULL_ROSENBROCK) g->variant = 1;
+      if (family == RWMPT_T_NEAL_FUNNEL) g->variant = 2;
     }
     const char* ev = getenv("RWMPT_VARIANT");
     if (ev) g->variant = atoi(ev);
@@ -161,6 +177,8 @@ static cudaError_t dispatch_mcmc(int family, const KernelArgs& a, const LaunchGe
     case RWMPT_T_IID_BETA: return launch_mcmc_iid_beta(a, g, ieee, st);
     case RWMPT_T_SCALED_MVN: return launch_mcmc_scaled_mvn(a, g, ieee, st);
     case RWMPT_T_MVN_DIAG: return launch_mcmc_mvn_diag(a, g, ieee, st);
+    case RWMPT_T_MVN_DENSE: return launch_mcmc_mvn_dense(a, g, ieee, st);
+    case RWMPT_T_SUPER_FUNNEL: return launch_mcmc_super_funnel(a, g, ieee, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -179,6 +197,8 @@ static cudaError_t dispatch_logp(int family, const float* P, int d, int E, int W
     case RWMPT_T_IID_BETA: return launch_logp_iid_beta(P, d, E, W, x, n, out, ieee, st);
     case RWMPT_T_SCALED_MVN: return launch_logp_scaled_mvn(P, d, E, W, x, n, out, ieee, st);
     case RWMPT_T_MVN_DIAG: return launch_logp_mvn_diag(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_MVN_DENSE: return launch_logp_mvn_dense(P, d, E, W, x, n, out, ieee, st);
+    case RWMPT_T_SUPER_FUNNEL: return launch_logp_super_funnel(P, d, E, W, x, n, out, ieee, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -307,6 +327,8 @@ __global__ void __launch_bounds__(128) proposal_kernel(int family, int d, int G,
     const bool row_ok = r < n;
     const unsigned long long rid = (unsigned long long)(row_base + (row_ok ? r : 0));
     float f = scale;
+    float zk[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // the lane's normals of pass 1, reused below when it owns a single block
+    const bool one_block = n_blk <= G;         // d <= 128: no second Philox pass
     if (family == RWMPT_P_UNIFORM_RADIUS) {
       // pass 1: squared norm of the row's normal vector (uniform.py:48-73: z / ||z|| * R * u^(1/d))
       float n2 = 0.0f;
@@ -316,8 +338,10 @@ __global__ void __launch_bounds__(128) proposal_kernel(int family, int d, int G,
         box_muller<false>(w.x, w.y, z[0], z[1]);
         box_muller<false>(w.z, w.w, z[2], z[3]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 4; ++q) {
           if (4 * b + q < d) n2 = fmaf(z[q], z[q], n2);
+          zk[q] = z[q];
+        }
       }
       for (int o = G >> 1; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFull, n2, o);
       const uint4 w = philox4x32_10(0xffffffffu, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
@@ -326,8 +350,12 @@ __global__ void __launch_bounds__(128) proposal_kernel(int family, int d, int G,
       f = scale * ex2_approx(lg2_approx(u01_from_bits(w.x)) / (float)d) * rcp_approx(safe);
     }
     for (int b = sub; b < n_blk; b += G) {
-      const uint4 w = philox4x32_10((unsigned)b, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
       float v[4];
+      if (family == RWMPT_P_UNIFORM_RADIUS && one_block) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = zk[q] * f;
+      } else {
+      const uint4 w = philox4x32_10((unsigned)b, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
       if (family == RWMPT_P_LAPLACE) {
         // laplace.py:47-69, as in pair_transform: 23 word bits -> r = 2u in [-1, 1); |increment| = -s ln(max(1 - |r|, 1e-6))
         const unsigned ww[4] = {w.x, w.y, w.z, w.w};
@@ -344,6 +372,7 @@ __global__ void __launch_bounds__(128) proposal_kernel(int family, int d, int G,
         box_muller<false>(w.z, w.w, v[2], v[3]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[q] *= f;
+      }
       }
       if (row_ok) {
         if (vec4) {
@@ -404,40 +433,6 @@ __global__ void __launch_bounds__(128) pt_swap_kernel(float* __restrict__ state,
   }
 }
 
-// ---- ESJD reduction over stored samples with the per-chain count of rows that moved: warp per row-pair, block
-// partials, one atomic per CTA (the form without the count is esjd_flat_kernel below) ---
-__global__ void __launch_bounds__(256) esjd_kernel(const float* __restrict__ samples, long long stride, long long first,
-                                                   long long n, int d, int ctas_per_chain, double* __restrict__ out,
-                                                   unsigned long long* __restrict__ moved) {
-  const long long chain = blockIdx.x / ctas_per_chain;
-  const int part = blockIdx.x % ctas_per_chain;
-  const float* base = samples + (chain * stride + first) * d;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  double acc = 0.0;
-  unsigned long long mv = 0;
-  for (long long m = 1 + part * n_warps + warp; m < n; m += (long long)ctas_per_chain * n_warps) {
-    float s = 0.0f;
-    for (int i = lane; i < d; i += 32) {
-      const float df = base[m * d + i] - base[(m - 1) * d + i];
-      s = fmaf(df, df, s);
-    }
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
-    acc += (double)s;
-    mv += s != 0.0f;
-  }
-  __shared__ double s_acc[8];
-  __shared__ unsigned long long s_mv[8];
-  if (lane == 0) { s_acc[warp] = acc; s_mv[warp] = mv; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    unsigned long long tm = 0;
-    for (int w = 0; w < n_warps; ++w) { t += s_acc[w]; tm += s_mv[w]; }
-    atomicAdd(&out[chain], t / (double)(n - 1));
-    if (moved) atomicAdd(&moved[chain], tm);
-  }
-}
-
 // ---- ESJD reduction, bandwidth form (no per-row output wanted): the chain's retained rows are one flat array f[n*d] and
 // sum_m ||x_m - x_{m-1}||^2 = sum_{j >= d} (f[j] - f[j-d])^2, so every thread streams aligned VW-float vectors of f and of
 // f shifted by one row (the shifted stream re-reads lines the first stream fetched d floats earlier: L1 / L2 hits, HBM
@@ -486,6 +481,95 @@ __global__ void __launch_bounds__(256) esjd_flat_kernel(const float* __restrict_
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += s_acc[w];
     atomicAdd(&out[chain], t / (double)(n - 1));
+  }
+}
+
+// ---- ESJD reduction WITH the per-chain count of rows that moved, bandwidth form.  Same streams as esjd_flat_kernel (aligned
+// VW-float vectors of a row and of its predecessor), but a warp owns whole rows: with vpr = d / VW vectors per row it maps
+// R = 32 / vpr rows onto R * vpr lanes per pass (vpr > 32: one row over ceil(vpr / 32) passes), so "did this row move" is
+// an OR over the row's lanes -- one ballot per pass, no shuffle, no shared memory -- and the count is a popcount of row
+// masks.  A row moved iff ANY coordinate differs from its predecessor (bitwise compare: an increment may be too small to
+// change the squared sum but still change the state).  Four passes in flight per warp.
+__device__ __forceinline__ bool differs(float4 a, float4 b) { return a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w; }
+__device__ __forceinline__ bool differs(float2 a, float2 b) { return a.x != b.x || a.y != b.y; }
+__device__ __forceinline__ bool differs(float a, float b) { return a != b; }
+template <int VW> __device__ __forceinline__ typename VecOf<VW>::T vec_zero();
+template <> __device__ __forceinline__ float4 vec_zero<4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <> __device__ __forceinline__ float2 vec_zero<2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ float vec_zero<1>() { return 0.f; }
+
+template <int VW>
+__global__ void __launch_bounds__(256) esjd_moved_kernel(const float* __restrict__ samples, long long stride, long long first,
+                                                         long long n, int d, int ctas_per_chain, double* __restrict__ out,
+                                                         unsigned long long* __restrict__ moved) {
+  using V = typename VecOf<VW>::T;
+  const long long chain = blockIdx.x / ctas_per_chain;
+  const int part = blockIdx.x % ctas_per_chain;
+  const V* base = reinterpret_cast<const V*>(samples + (chain * stride + first) * d);   // row m starts at base + m * vpr
+  const int vpr = d / VW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const long long jumps = n - 1;                                   // jump j compares row j + 1 with row j
+  const long long per = (jumps + ctas_per_chain - 1) / ctas_per_chain;
+  const long long lo = part * per, hi = lo + per < jumps ? lo + per : jumps;
+  double acc = 0.0;
+  unsigned long long mv = 0;
+  if (vpr <= 32) {
+    const int R = 32 / vpr;                                        // rows per pass
+    const int r = lane / vpr, vec = lane - r * vpr;
+    const bool lane_on = lane < R * vpr;
+    const unsigned row_mask = vpr == 32 ? 0xffffffffu : ((1u << vpr) - 1u);
+    constexpr int U = 4;                                           // passes in flight
+    for (long long j0 = lo + (long long)warp * R * U; j0 < hi; j0 += (long long)n_warps * R * U) {
+      V c[U], p[U];
+      bool on[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long j = j0 + (long long)u * R + r;
+        on[u] = lane_on && j < hi;
+        c[u] = on[u] ? base[(j + 1) * vpr + vec] : vec_zero<VW>();
+        p[u] = on[u] ? base[j * vpr + vec] : vec_zero<VW>();
+      }
+      float s = 0.0f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        s += sqdiff(c[u], p[u]);
+        const unsigned b = __ballot_sync(kFull, on[u] && differs(c[u], p[u]));
+        for (int q = 0; q < R; ++q) mv += ((b >> (q * vpr)) & row_mask) != 0u;   // uniform across the warp
+      }
+      acc += (double)s;
+    }
+    if (lane != 0) mv = 0;                                          // every lane counted the same rows
+  } else {
+    const int passes = (vpr + 31) / 32;
+    for (long long j = lo + warp; j < hi; j += n_warps) {
+      float s = 0.0f;
+      unsigned any = 0u;
+      for (int q = 0; q < passes; ++q) {
+        const int vec = q * 32 + lane;
+        const bool on = vec < vpr;
+        const V c = on ? base[(j + 1) * vpr + vec] : vec_zero<VW>();
+        const V p = on ? base[j * vpr + vec] : vec_zero<VW>();
+        s += sqdiff(c, p);
+        any |= __ballot_sync(kFull, on && differs(c, p));
+      }
+      acc += (double)s;
+      mv += (lane == 0 && any != 0u) ? 1ull : 0ull;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(kFull, acc, o);
+    mv += __shfl_xor_sync(kFull, mv, o);
+  }
+  __shared__ double s_acc[8];
+  __shared__ unsigned long long s_mv[8];
+  if (lane == 0) { s_acc[warp] = acc; s_mv[warp] = mv; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    unsigned long long tm = 0;
+    for (int w = 0; w < n_warps; ++w) { t += s_acc[w]; tm += s_mv[w]; }
+    atomicAdd(&out[chain], t / (double)(n - 1));
+    atomicAdd(&moved[chain], tm);
   }
 }
 
@@ -685,11 +769,18 @@ int rwmpt_esjd_reduce(const float* samples, int64_t n_chains, int64_t stride, in
     return RWMPT_OK;
   }
   long long want = (148LL * 8 + n_chains - 1) / n_chains;  // enough CTAs to fill the machine
-  long long maxp = (n - 1 + 7) / 8;
+  long long maxp = (n - 1 + 255) / 256;                    // at least ~256 jumps per CTA
   int cpc = (int)(want < 1 ? 1 : (want > maxp ? maxp : want));
   if (cpc < 1) cpc = 1;
   if (n_chains * cpc > 2147483647LL) return fail(RWMPT_ENOTSUP, "too many chains for esjd_reduce");
-  esjd_kernel<<<(unsigned)(n_chains * cpc), 256, 0, st>>>(samples, stride, first, n, dim, cpc, esjd_out, moved_out);
+  {
+    const uintptr_t p = reinterpret_cast<uintptr_t>(samples);
+    const int vw = (dim % 4 == 0 && p % 16 == 0) ? 4 : ((dim % 2 == 0 && p % 8 == 0) ? 2 : 1);
+    const unsigned grid = (unsigned)(n_chains * cpc);
+    if (vw == 4) esjd_moved_kernel<4><<<grid, 256, 0, st>>>(samples, stride, first, n, dim, cpc, esjd_out, moved_out);
+    else if (vw == 2) esjd_moved_kernel<2><<<grid, 256, 0, st>>>(samples, stride, first, n, dim, cpc, esjd_out, moved_out);
+    else esjd_moved_kernel<1><<<grid, 256, 0, st>>>(samples, stride, first, n, dim, cpc, esjd_out, moved_out);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "esjd kernel launch");
   return RWMPT_OK;

@@ -2,7 +2,6 @@
 // plus the tuned (compile-time lanes-per-chain / proposal family) variants used by the BASELINE workloads.
 #include "rwmpt_launch.cuh"
 #define TUNED_LIST(cls)                                             \
-  RWMPT_TUNED_CASE_V(cls, 13, 8, 0, 1) RWMPT_TUNED_CASE_V(cls, 13, 8, 0, 2) RWMPT_TUNED_CASE_V(cls, 13, 8, 0, 3) \
-  RWMPT_TUNED_CASE_V(cls, 13, 8, 0, 4) RWMPT_TUNED_CASE(cls, 13, 8, 0)
+  RWMPT_TUNED_CASE_V(cls, 13, 8, 0, 1) RWMPT_TUNED_CASE_V(cls, 13, 8, 0, 2) RWMPT_TUNED_CASE(cls, 13, 8, 0)
 RWMPT_DEFINE_TUNED(rwmpt::NealFunnel, TUNED_LIST)
 RWMPT_DEFINE_FAMILY(neal_funnel, NealFunnel)

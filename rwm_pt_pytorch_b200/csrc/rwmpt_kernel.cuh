@@ -889,10 +889,13 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
 //
 // VARIANT (tuned instantiations only): 0 = three-stage pipeline, any CTA size; 1 / 2 = lean loop for one-warp CTAs compiled
 // for >= 16 / >= 12 resident CTAs per SM (<= 128 / <= 168 registers: 4 / 3 warps per scheduler); 3 / 4 = the same with ten
-// plain Philox rounds per call instead of the PhiloxPairGen invariants (fewer live registers).
-__host__ __device__ constexpr int variant_threads(int v) { return v == 0 ? kMaxCtaThreads : 32; }
-__host__ __device__ constexpr int variant_min_ctas(int v) { return (v == 1 || v == 3) ? 16 : ((v == 2 || v == 4) ? 12 : 1); }
-__host__ __device__ constexpr int variant_leanmode(int v) { return v == 0 ? 0 : (v <= 2 ? 1 : 2); }
+// plain Philox rounds per call instead of the PhiloxPairGen invariants (fewer live registers); 5 / 6 = lean loop for CTAs of
+// up to 64 threads (stored trajectories allowed), no register cap / <= 168 registers.
+__host__ __device__ constexpr int variant_threads(int v) { return v == 0 ? kMaxCtaThreads : (v >= 5 ? 64 : 32); }
+__host__ __device__ constexpr int variant_min_ctas(int v) {
+  return (v == 1 || v == 3) ? 16 : ((v == 2 || v == 4) ? 12 : (v == 6 ? 6 : 1));
+}
+__host__ __device__ constexpr int variant_leanmode(int v) { return v == 0 ? 0 : ((v <= 2 || v >= 5) ? 1 : 2); }
 
 template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE, int VARIANT = 0>
 __global__ void __launch_bounds__(variant_threads(VARIANT), variant_min_ctas(VARIANT)) mcmc_kernel(const KernelArgs a) {

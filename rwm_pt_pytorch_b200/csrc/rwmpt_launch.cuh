@@ -11,8 +11,10 @@ namespace rwmpt {
 #define RWMPT_FAST_E_LIST(X) X(5)
 #define RWMPT_IEEE_E_LIST(X) X(5)
 #else
-#define RWMPT_FAST_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
-#define RWMPT_IEEE_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13)
+// (25: few lanes per chain for LONG ladders -- a ladder's n_temps * lanes threads must fit one CTA of kMaxCtaThreads, so
+// d = 100 runs ladders of up to 64 temperatures on 25 coordinates x 4 lanes -- and dimensions up to 800)
+#define RWMPT_FAST_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13) X(25)
+#define RWMPT_IEEE_E_LIST(X) X(1) X(2) X(3) X(4) X(5) X(8) X(13) X(25)
 #endif
 
 template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, bool STORE, int VARIANT = 0>
@@ -37,7 +39,12 @@ struct SplitStore<RoughCarpetPlain> {
 
 template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, int VARIANT = 0>
 cudaError_t launch_mcmc_one(const KernelArgs& a_in, const LaunchGeom& g, cudaStream_t st) {
-  if constexpr (VARIANT != 0) {
+  if constexpr (VARIANT >= 5) {
+    // lean variants for CTAs of up to 64 threads, with or without retained samples
+    if (g.threads > 64) return launch_mcmc_one<Target, E, IEEE, WT, PF, EXACT, TEST, 0>(a_in, g, st);
+    if (a_in.samples != nullptr) return launch_mcmc_store<Target, E, IEEE, WT, PF, EXACT, TEST, true, VARIANT>(a_in, g, st);
+    return launch_mcmc_store<Target, E, IEEE, WT, PF, EXACT, TEST, false, VARIANT>(a_in, g, st);
+  } else if constexpr (VARIANT != 0) {
     // lean variants: accumulators-only runs of one-warp CTAs; anything else takes the pipelined kernel of the same geometry
     if (a_in.samples != nullptr || g.threads != 32) return launch_mcmc_one<Target, E, IEEE, WT, PF, EXACT, TEST, 0>(a_in, g, st);
     return launch_mcmc_store<Target, E, IEEE, WT, PF, EXACT, TEST, false, VARIANT>(a_in, g, st);
@@ -177,7 +184,9 @@ namespace rwmpt {
   X(iid_gamma, IIDGamma)                     \
   X(iid_beta, IIDBeta)                       \
   X(scaled_mvn, ScaledMVN)                   \
-  X(mvn_diag, MVNDiag)
+  X(mvn_diag, MVNDiag)                       \
+  X(mvn_dense, MVNDense)                     \
+  X(super_funnel, SuperFunnel)
 
 #define X(name, cls)                                                                                         \
   cudaError_t launch_mcmc_##name(const KernelArgs& a, const LaunchGeom& g, bool ieee, cudaStream_t st);       \
@@ -205,6 +214,11 @@ RWMPT_FAMILY_LIST(X)
   if (a.target_plain && g.E == e && g.W == w && a.prop_family == pf) {                             \
     if (a.dim == e * w) return launch_mcmc_one<plain, e, false, w, pf, true, false>(a, g, st);    \
     return launch_mcmc_one<plain, e, false, w, pf, false, false>(a, g, st);                       \
+  }
+#define RWMPT_TUNED_PLAIN_CASE_V(cls, plain, e, w, pf, v)                                               \
+  if (g.variant == v && a.target_plain && g.E == e && g.W == w && a.prop_family == pf) {              \
+    if (a.dim == e * w) return launch_mcmc_one<plain, e, false, w, pf, true, false, v>(a, g, st);     \
+    return launch_mcmc_one<plain, e, false, w, pf, false, false, v>(a, g, st);                        \
   }
 #define RWMPT_DEFINE_TUNED(cls, LIST)                                                              \
   namespace rwmpt {                                                                                \

@@ -532,4 +532,126 @@ struct MVNDiag {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Targets whose density couples every coordinate with every other.  A lane needs the chain's whole
+// state: the lanes of the chain all-gather it with shuffles into a per-thread array (dynamic indexing: local memory,
+// L1-resident).  Dimension limit kMaxGather.  These are functional rather than tuned: the matvec / data loop per step is
+// the cost the reference pays too.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxGather = 128;
+
+template <int E, class C>
+__device__ __forceinline__ void gather_all(const float (&v)[E], const C& c, float* all) {
+  for (int s = 0; s < c.W; ++s) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float t = __shfl_sync(kFull, v[e], c.leader + s);
+      if (s * E + e < kMaxGather) all[s * E + e] = t;
+    }
+  }
+}
+
+// ---- MultivariateNormalTorch.log_density with a general (dense) covariance, multivariate_normal_torch.py:62-92:
+// temp = centered @ cov_inv; q = sum(temp * centered); out = -0.5 q + log_norm_const.
+// P[0] log norm const; P[16..16+d) mean; then cov_inv row-major (d x d).
+template <int E, bool IEEE>
+struct MVNDense {
+  using M = Mth<IEEE>;
+  float lnc;
+  float mean[E];
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) {
+    lnc = c.P[0];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      mean[e] = (i < c.d) ? c.P[RWMPT_PARAM_HEADER + i] : 0.0f;
+    }
+  }
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
+    float cen[E], all[kMaxGather];
+#pragma unroll
+    for (int e = 0; e < E; ++e) cen[e] = c.ok(e) ? M::sub(x[e], mean[e]) : 0.0f;
+    gather_all(cen, c, all);
+    const float* A = c.P + RWMPT_PARAM_HEADER + c.d;
+    float part = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.base + e;
+      if (i < c.d) {
+        float t = 0.0f;
+        for (int s = 0; s < c.W; ++s)
+          for (int q = 0; q < E; ++q) {
+            const int j = s * E + q;                       // coordinate held by lane s, slot q
+            if (j < c.d) t = IEEE ? M::add(t, M::mul(all[j], __ldg(A + (size_t)j * c.d + i))) : fmaf(all[j], __ldg(A + (size_t)j * c.d + i), t);
+          }
+        part = IEEE ? M::add(part, M::mul(t, cen[e])) : fmaf(t, cen[e], part);
+      }
+    }
+    return M::add(M::mul(-0.5f, group_sum(part, c)), lnc);
+  }
+};
+
+// ---- SuperFunnelTorch.log_density, funnel_torch.py:193-291 (hierarchical logistic regression).
+// theta = (alpha[J], beta[J][K], mu_alpha, mu_beta[K], tau_alpha, tau_beta).
+// P[0] J, P[1] K, P[2] prior hyper-mean variance, P[3] its log, P[4] prior tau scale, P[5] its log, P[6] log 2pi, P[7] log 2,
+// P[8] log pi, P[9] number of observations N; then N records of (group j, y, x[K]) after the header.
+template <int E, bool IEEE>
+struct SuperFunnel {
+  using M = Mth<IEEE>;
+  int J, K, N;
+  float hv, lhv, ts, lts, l2p, l2, lpi;
+  template <class C>
+  __device__ __forceinline__ void init(const C& c) {
+    const float* P = c.P;
+    J = (int)P[0]; K = (int)P[1]; hv = P[2]; lhv = P[3]; ts = P[4]; lts = P[5]; l2p = P[6]; l2 = P[7]; lpi = P[8]; N = (int)P[9];
+  }
+  static __device__ __forceinline__ float log_sigmoid(float z) {   // F.logsigmoid: min(z, 0) - log1p(exp(-|z|))
+    const float a = fabsf(z);
+    return IEEE ? fminf(z, 0.0f) - log1pf(expf(-a)) : fminf(z, 0.0f) - M::log(1.0f + M::exp(-a));
+  }
+  template <class C>
+  __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
+    float th[kMaxGather];
+    gather_all(x, c, th);
+    const int o_ma = J + J * K, o_mb = o_ma + 1, o_ta = o_mb + K, o_tb = o_ta + 1;
+    const float mu_a = th[o_ma], tau_a = th[o_ta], tau_b = th[o_tb];
+    // likelihood: the chain's lanes share the observations (:236-249)
+    const float* D = c.P + RWMPT_PARAM_HEADER;
+    float ll = 0.0f;
+    for (int n = c.sub; n < N; n += c.W) {
+      const float* rec = D + (size_t)n * (K + 2);
+      const int j = (int)rec[0];
+      const float y = rec[1];
+      float eta = th[j];
+      for (int k = 0; k < K; ++k) eta = fmaf(rec[2 + k], th[J + j * K + k], eta);
+      ll += y * log_sigmoid(eta) + (1.0f - y) * log_sigmoid(-eta);
+    }
+    ll = group_sum(ll, c);
+    if (!(tau_a > 1e-9f) || !(tau_b > 1e-9f)) return RWMPT_NEG_INF;                       // :225-227
+    // priors, evaluated by every lane on the gathered state (identical values on all lanes) (:256-291)
+    float pa = 0.0f, pb = 0.0f;
+    const float ita2 = 1.0f / (tau_a * tau_a), itb2 = 1.0f / (tau_b * tau_b), lta = M::log(tau_a), ltb = M::log(tau_b);
+    for (int j = 0; j < J; ++j) {
+      const float da = th[j] - mu_a;
+      pa += -0.5f * l2p - lta - 0.5f * da * da * ita2;
+      float sq = 0.0f;
+      for (int k = 0; k < K; ++k) {
+        const float db = th[J + j * K + k] - th[o_mb + k];
+        sq = fmaf(db, db, sq);
+      }
+      pb += -0.5f * (float)K * l2p - (float)K * ltb - 0.5f * sq * itb2;
+    }
+    float smb = 0.0f;
+    for (int k = 0; k < K; ++k) smb = fmaf(th[o_mb + k], th[o_mb + k], smb);
+    const float p_ma = -0.5f * l2p - 0.5f * lhv - 0.5f * mu_a * mu_a / hv;
+    const float p_mb = -0.5f * (float)K * l2p - 0.5f * (float)K * lhv - 0.5f * smb / hv;
+    const float ra = tau_a / ts, rb = tau_b / ts;
+    const float p_ta = l2 - lpi - lts - (IEEE ? log1pf(ra * ra) : M::log(1.0f + ra * ra));
+    const float p_tb = l2 - lpi - lts - (IEEE ? log1pf(rb * rb) : M::log(1.0f + rb * rb));
+    return ((((((ll + pa) + pb) + p_ma) + p_mb) + p_ta) + p_tb);
+  }
+};
+
 }  // namespace rwmpt

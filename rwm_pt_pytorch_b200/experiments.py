@@ -58,7 +58,18 @@ def get_target_distribution(name: str, dim: int, device=None, pt: bool = False, 
         return td.NealFunnelTorch(dim, mu_v=kwargs.get('mu_v', 0.0), sigma_v_sq=kwargs.get('sigma_v_sq', 9.0),
                                   mu_z=kwargs.get('mu_z', 0.0), device=device)
     if name == "SuperFunnel":
-        return td.SuperFunnelTorch()
+        # synthetic data exactly as the reference generates it (experiment_RWM_GPU.py:95-120), on the CPU generator so that
+        # the data do not depend on the device
+        J, K, n_per = kwargs.get('J', 5), kwargs.get('K', 3), kwargs.get('n_per_group', 20)
+        torch.manual_seed(42)
+        X_data, Y_data = [], []
+        for _ in range(J):
+            X_j = torch.randn(n_per, K)
+            Y_j = torch.bernoulli(torch.sigmoid(0.5 * torch.sum(X_j, dim=1)))
+            X_data.append(X_j)
+            Y_data.append(Y_j)
+        return td.SuperFunnelTorch(J, K, X_data, Y_data, prior_hypermean_std=kwargs.get('prior_hypermean_std', 10.0),
+                                   prior_tau_scale=kwargs.get('prior_tau_scale', 2.5), device=device)
     raise ValueError("Unknown target distribution name")
 
 
@@ -108,7 +119,9 @@ def run_rwm_study(dim, target_name="MultivariateNormal", num_iters=100000, var_m
         'max_acceptance_rate': acceptance_rates[best], 'max_scale_param': float(scales[best]),
         'expected_squared_jump_distances': esjds, 'acceptance_rates': acceptance_rates,
         'scale_param_range': scales.tolist(), 'times': [total_time / num_values] * num_values,
-        # appended keys
+        # appended keys ('var_value_range' / 'max_variance_value': the names the reference's earlier files and its
+        # data/average_seeds.py use for the same two fields)
+        'var_value_range': scales.tolist(), 'max_variance_value': float(scales[best]),
         'chains_per_value': chains_per_value, 'acceptance_rate_se': _se(acc).tolist(), 'esjd_se': _se(esjd).tolist(),
         'burn_in': burn_in, 'chain_steps_per_sec': n_chains * (num_iters + burn_in) / total_time,
     }

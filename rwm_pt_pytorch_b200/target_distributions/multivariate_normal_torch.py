@@ -1,7 +1,6 @@
 """Gaussian targets (reference: target_distributions/multivariate_normal_torch.py):
-`MultivariateNormalTorch` (:5-134) -- identity / diagonal covariance run in the fused kernel; a general dense
-covariance is a matvec per step and is out of scope (NotImplementedError) -- and
-`ScaledMultivariateNormalTorch` (:137-295)."""
+`MultivariateNormalTorch` (:5-134) -- identity / diagonal covariance runs the lean diagonal functor (`MVNDiag`), a general
+dense covariance the gather-and-matvec functor (`MVNDense`, dim <= 128) -- and `ScaledMultivariateNormalTorch` (:137-295)."""
 import numpy as np
 import torch
 
@@ -18,9 +17,12 @@ class MultivariateNormalTorch(_MoveTensorsMixin, TorchTargetDistribution):
         self.name = "MultivariateNormalTorch"
         mean = torch.zeros(dim, dtype=torch.float32) if mean is None else torch.as_tensor(mean, dtype=torch.float32)
         cov = torch.eye(dim, dtype=torch.float32) if cov is None else torch.as_tensor(cov, dtype=torch.float32)
-        if not torch.equal(torch.diag(torch.diagonal(cov)), cov):
-            raise NotImplementedError("MultivariateNormalTorch with a non-diagonal covariance is outside the fused "
-                                      "sm_100a sampling path (dense matvec per step); see DESIGN.md, out of scope.")
+        self.is_diagonal = bool(torch.equal(torch.diag(torch.diagonal(cov)), cov))
+        if not self.is_diagonal:
+            if dim > 128:
+                raise NotImplementedError("MultivariateNormalTorch with a dense covariance supports dim <= 128 "
+                                          "(every lane of a chain gathers the whole state)")
+            self.family_id = _lib.T_MVN_DENSE
         self.mean = mean.to(self.device)
         self.cov = cov.to(self.device)
         self.cov_inv = torch.linalg.inv(self.cov)
@@ -29,9 +31,13 @@ class MultivariateNormalTorch(_MoveTensorsMixin, TorchTargetDistribution):
         self.log_norm_const = -0.5 * (dim * log_2pi + torch.log(self.cov_det))
 
     def _pack(self):
+        if not self.is_diagonal:
+            return torch.cat([self._header(float(self.log_norm_const)), self.mean.cpu(), self.cov_inv.cpu().reshape(-1)])
         return torch.cat([self._header(float(self.log_norm_const)), self.mean.cpu(), torch.diagonal(self.cov_inv).cpu()])
 
     def spec(self):
+        if not self.is_diagonal:
+            return dict(family="mvn_dense", mean=t2n(self.mean), cov_inv=t2n(self.cov_inv), log_norm_const=t2n(self.log_norm_const))
         return dict(family="mvn_diag", mean=t2n(self.mean), prec=t2n(torch.diagonal(self.cov_inv)),
                     log_norm_const=t2n(self.log_norm_const))
 
@@ -43,6 +49,8 @@ class MultivariateNormalTorch(_MoveTensorsMixin, TorchTargetDistribution):
 
     def draw_samples_torch(self, n_samples, beta=1.0):
         z = torch.randn(n_samples, self.dim, device=self.device, dtype=torch.float32)
+        if not self.is_diagonal:                                           # :101-121: mean + z @ chol(cov / beta)^T
+            return self.mean.unsqueeze(0) + torch.matmul(z, torch.linalg.cholesky(self.cov / beta).T)
         return self.mean.unsqueeze(0) + z * torch.sqrt(torch.diagonal(self.cov) / beta).unsqueeze(0)
 
 

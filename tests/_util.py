@@ -86,6 +86,16 @@ def make_product_targets():
         6, mean=[0.5, -1.0, 0.0, 2.0, 0.25, -0.75], cov=np.diag([0.5, 2.0, 1.0, 4.0, 0.25, 1.5]).tolist(), device=CPU)
     d["full_rosenbrock_d100"] = td.FullRosenbrockTorch(100, device=CPU)
     d["neal_funnel_d100"] = td.NealFunnelTorch(100, device=CPU)
+    dense_mean = [0.3 * ((-1) ** i) * (i % 4) for i in range(12)]
+    dense_cov = [[(0.7 ** abs(i - j)) * (1.0 + 0.1 * min(i, j)) for j in range(12)] for i in range(12)]
+    d["mvn_dense_d12"] = td.MultivariateNormalTorch(12, mean=dense_mean, cov=dense_cov, device=CPU)
+    g = torch.Generator().manual_seed(42)
+    X, Y = [], []
+    for _ in range(5):
+        Xj = torch.randn(20, 3, generator=g)
+        X.append(Xj)
+        Y.append(torch.bernoulli(torch.sigmoid(0.5 * torch.sum(Xj, dim=1)), generator=g))
+    d["super_funnel_j5k3"] = td.SuperFunnelTorch(5, 3, X, Y, prior_hypermean_std=10.0, prior_tau_scale=2.5, device=CPU)
     return d
 
 
@@ -117,7 +127,7 @@ def make_keys():
             "even_rosenbrock_d10", "even_rosenbrock_d20", "even_rosenbrock_d30", "hybrid_rosenbrock_n3x5",
             "hybrid_rosenbrock_n4x2", "neal_funnel_d10", "neal_funnel_d1", "hypercube_pm1_d5", "hypercube_01_d4",
             "iid_gamma_d8", "iid_beta_d8", "scaled_mvn_d12", "mvn_identity_d50", "mvn_diag_d6", "full_rosenbrock_d100",
-            "neal_funnel_d100"]
+            "neal_funnel_d100", "mvn_dense_d12", "super_funnel_j5k3"]
 
 
 def specs_equal(a, b):

@@ -93,9 +93,16 @@ def spec_of(t) -> dict:
     if n == "ScaledMultivariateNormalTorch":
         return dict(family="scaled_mvn", c=t2n(t.scaling_factors), log_norm_const=t2n(t.log_norm_const))
     if n == "MultivariateNormalTorch":
+        if not torch.allclose(torch.diag(torch.diagonal(t.cov_inv)), t.cov_inv):
+            return dict(family="mvn_dense", mean=t2n(t.mean), cov_inv=t2n(t.cov_inv), log_norm_const=t2n(t.log_norm_const))
         prec = t2n(torch.diagonal(t.cov_inv))
-        assert torch.allclose(torch.diag(torch.diagonal(t.cov_inv)), t.cov_inv), "golden cases use diagonal cov"
         return dict(family="mvn_diag", mean=t2n(t.mean), prec=prec, log_norm_const=t2n(t.log_norm_const))
+    if n == "SuperFunnelTorch":
+        rec = torch.cat([torch.cat([torch.full((t.Y_data[j].shape[0], 1), float(j)), t.Y_data[j].reshape(-1, 1), t.X_data[j]], dim=1)
+                         for j in range(t.J)], dim=0)
+        return dict(family="super_funnel", J=np.int64(t.J), K=np.int64(t.K), records=t2n(rec), hyper_var=t2n(t.prior_hypermean_var),
+                    log_hyper_var=t2n(t.log_prior_hypermean_var), tau_scale=t2n(t.prior_tau_scale),
+                    log_tau_scale=t2n(t.log_prior_tau_scale), log_2pi=t2n(t.log_2_pi), log_2=t2n(t.log_2), log_pi=t2n(t.log_pi))
     raise ValueError(n)
 
 
@@ -108,6 +115,20 @@ def save(name, spec, **arrays):
 
 
 # --- targets used by the cases --------------------------------------------------------------
+DENSE_MEAN = [0.3 * ((-1) ** i) * (i % 4) for i in range(12)]
+DENSE_COV = [[(0.7 ** abs(i - j)) * (1.0 + 0.1 * min(i, j)) for j in range(12)] for i in range(12)]
+
+
+def make_super_funnel(cls, J=5, K=3, n_per=20):
+    g = torch.Generator().manual_seed(42)
+    X, Y = [], []
+    for _ in range(J):
+        Xj = torch.randn(n_per, K, generator=g)
+        X.append(Xj)
+        Y.append(torch.bernoulli(torch.sigmoid(0.5 * torch.sum(Xj, dim=1)), generator=g))
+    return cls(J, K, X, Y, prior_hypermean_std=10.0, prior_tau_scale=2.5, device=CPU)
+
+
 def make_targets():
     torch.manual_seed(1234)  # fixes the random scaling factors of the *Scaled targets
     d = {}
@@ -139,6 +160,10 @@ def make_targets():
     # so appending them leaves every earlier fixture bit-identical
     d["full_rosenbrock_d100"] = td.FullRosenbrockTorch(100, device=CPU)
     d["neal_funnel_d100"] = td.NealFunnelTorch(100, device=CPU)
+    # dense-covariance Gaussian (AR(1)-like covariance, not diagonal) and the hierarchical logistic
+    # "super funnel" on the synthetic data of experiment_RWM_GPU.py:95-120 (own generator: the global stream is untouched)
+    d["mvn_dense_d12"] = td.MultivariateNormalTorch(12, mean=DENSE_MEAN, cov=DENSE_COV, device=CPU)
+    d["super_funnel_j5k3"] = make_super_funnel(td.SuperFunnelTorch)
     return d
 
 
@@ -159,6 +184,11 @@ def gen_logp(name, target):
         x = torch.randn(n, dim, generator=g) * 1.5 + 0.5
     elif tn == "NealFunnelTorch":
         x = torch.randn(n, dim, generator=g) * 3.0
+    elif tn == "SuperFunnelTorch":
+        x = torch.randn(n, dim, generator=g) * 1.5
+        x[:, -2:] = x[:, -2:].abs() + 0.05            # taus in the support ...
+        x[:6, -1] = torch.tensor([-0.3, 0.0, 1e-10, 2.0, 0.5, 1.0])   # ... except a few rows (-> -inf)
+        x[3:6, -2] = torch.tensor([-1.0, 0.0, 3.0])
     else:
         x = torch.randn(n, dim, generator=g) * 6.0
     x = x.to(torch.float32)
@@ -190,12 +220,14 @@ def gen_proposals():
 
 
 # --- RWM: run RandomWalkMH_GPU_Optimized on the CPU device and capture everything ---------------
-def gen_rwm(name, target, n_samples, burn_in, seed, var=None, proposal=None, beta=1.0):
+def gen_rwm(name, target, n_samples, burn_in, seed, var=None, proposal=None, beta=1.0, x0=None):
     np.random.seed(seed)  # initial state of the "else" branch comes from NumPy's global RNG
     with quiet():
         algo = ref_rwm_mod.RandomWalkMH_GPU_Optimized(
             dim=target.dim, var=var, target_dist=target, beta=beta, burn_in=burn_in, device="cpu",
             pre_allocate_steps=n_samples, proposal_distribution=proposal)
+    if x0 is not None:       # generate_samples starts from chain[-1] (rwm_gpu_optimized.py:431-434)
+        algo.chain = [np.asarray(x0, dtype=np.float64)]
     cap = {"acc": []}
     orig_pre = algo._precompute_all_randoms
 
@@ -390,6 +422,9 @@ def main():
     gen_rwm("rwm_rough_carpet_d20_uniform", T["rough_carpet_d20"], 400, 50, seed=24,
             proposal=UniformRadiusProposal(20, 2.5, 1.0, CPU, torch.float32))
 
+    gen_rwm("rwm_mvn_dense_d12", T["mvn_dense_d12"], 400, 50, seed=27, var=0.5)
+    sf0 = np.zeros(T["super_funnel_j5k3"].dim); sf0[-2:] = 1.0     # the default start (1e-8 N(0,1)) sits in the funnel's neck
+    gen_rwm("rwm_super_funnel_j5k3", T["super_funnel_j5k3"], 500, 0, seed=28, var=0.02, x0=sf0)
     # BASELINE config 5: d = 100, at one point of each variance sweep (experiment_RWM_GPU.py:202-218: variance = x^2 / dim)
     gen_rwm("rwm_full_rosenbrock_d100", T["full_rosenbrock_d100"], 500, 100, seed=25, var=0.340769 ** 2 / 100)
     gen_rwm("rwm_neal_funnel_d100", T["neal_funnel_d100"], 500, 100, seed=26, var=1.699744 ** 2 / 100)

@@ -154,7 +154,7 @@ def test_reference_average_seeds_tool_consumes_driver_output(tmp_path):
             for s in (1, 2, 3)]
     pts = [run_pt_study(8, "ThreeMixture", num_iters=4000, seed=s, num_values=4, N_samples_swap_est=5000, iterative_tolerance=0.01,
                         ladders_per_value=4, swap_every=10, out_dir=str(tmp_path)) for s in (1, 2)]
-    for pattern, runs, key in (("EvenRosenbrock_Normal_RWM_GPU_dim10_20000iters", outs, "scale_param_range"),
+    for pattern, runs, key in (("EvenRosenbrock_Normal_RWM_GPU_dim10_20000iters", outs, "var_value_range"),
                                ("ThreeMixture_PT_GPU_dim8_4000iters", pts, "swap_acceptance_rates_range")):
         p = subprocess.run([sys.executable, tool, "--pattern", pattern, "--data_dir", str(tmp_path), "--output_dir", str(tmp_path)],
                            capture_output=True, text=True, timeout=300)
@@ -165,6 +165,8 @@ def test_reference_average_seeds_tool_consumes_driver_output(tmp_path):
         want = np.mean([r["acceptance_rates"] for r in runs], axis=0)
         np.testing.assert_allclose(avg["acceptance_rates"], want, rtol=1e-9)
         np.testing.assert_allclose(avg[key], runs[0][key], rtol=1e-12)
+        assert avg["num_files_averaged"] == len(runs) and avg["dimension"] == runs[0]["dimension"]
+        np.testing.assert_allclose(avg["max_esjd"], np.mean([r["max_esjd"] for r in runs]), rtol=1e-9)
 
 
 def test_benchmark_performance_schema_and_rates():

@@ -206,7 +206,9 @@ def test_rwm_batch_matches_oracle(case):
 
 @pytest.mark.parametrize("swap_mode", ["reference", "exchange"])
 @pytest.mark.parametrize("case", [("rough_carpet_d20", 20, 8, 0), ("rough_carpet_d20", 20, 5, 2), ("three_mixture_d10", 10, 3, 0),
-                                  ("even_rosenbrock_d10", 10, 13, 1), ("neal_funnel_d10", 10, 40, 4)])
+                                  ("even_rosenbrock_d10", 10, 13, 1), ("neal_funnel_d10", 10, 40, 4),
+                                  # a 64-temperature ladder at d = 100 (refused): 25 coordinates x 4 lanes, 256 threads
+                                  ("full_rosenbrock_d100", 100, 64, 0)])
 def test_pt_batch_matches_oracle(case, swap_mode):
     """12 ladders, ragged ladder sizes (K not a power of two, K*lanes > one warp), both swap semantics."""
     key, d, K, lanes = case
@@ -221,10 +223,21 @@ def test_pt_batch_matches_oracle(case, swap_mode):
     std = np.sqrt(np.asarray([np.float32(0.5 / b) for b in betas], np.float32))
     if key == "even_rosenbrock_d10":
         std = std * 0.1
+    if key == "full_rosenbrock_d100":
+        std = std * 0.05
+        L, T = 4, 60
+        x0, u = x0[:L], None
     inc = (rs.randn(T, L, K, d).astype(np.float32) * std[None, None, :, None]).astype(np.float32)
     u = rs.rand(T, L, K).astype(np.float32)
     R = sum(1 for s in range(1, T + 1) if s % se == 0 and s > burn)
     su = rs.rand(R, L, K - 1).astype(np.float32)
+    if key == "full_rosenbrock_d100":       # the same long ladder on the fast-math kernel (native Philox): runs, swaps, moves
+        fast = PT(d, 0.0025, t, beta_ladder=betas, swap_every=se, burn_in=burn, device=dev, num_ladders=8, store="none",
+                  swap_mode=swap_mode, seed=5)
+        assert fast._batch.geometry() == (25, 4)
+        fast.generate_samples(400)
+        assert fast.num_swap_attempts == (410 // se - burn // se) * (K - 1) * 8 and fast.swap_acceptance_rate > 0.2
+        assert torch.isfinite(fast.current_states).all() and float(fast.mh_acceptance_rates.mean()) > 0.05
     algo = PT(d, 0.5, t, beta_ladder=betas, swap_every=se, burn_in=burn, device=dev, num_ladders=L, store="all",
               math_mode="ieee", swap_mode=swap_mode, initial_states=x0, lanes_per_chain=lanes)
     dec, sdec = algo.run_injected(inc.reshape(T, L * K, d), u.reshape(T, L * K), su)

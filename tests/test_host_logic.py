@@ -88,10 +88,16 @@ def test_target_names_and_errors():
         td.FullRosenbrockTorch(1, device=CPU)
     with pytest.raises(ValueError):
         td.RoughCarpetDistributionTorch(3, device=CPU, mode_weights=[0.5, 0.5, 0.5])
+    dense = td.MultivariateNormalTorch(2, cov=[[1.0, 0.5], [0.5, 1.0]], device=CPU)        # dense covariance: its own functor
+    assert dense.family_id == _lib.T_MVN_DENSE and dense.pack().numel() == _lib.PARAM_HEADER + 2 + 4
+    assert td.MultivariateNormalTorch(2, device=CPU).family_id == _lib.T_MVN_DIAG
     with pytest.raises(NotImplementedError):
-        td.MultivariateNormalTorch(2, cov=[[1.0, 0.5], [0.5, 1.0]], device=CPU)
-    with pytest.raises(NotImplementedError):
-        td.SuperFunnelTorch(2, 2, [], [])
+        td.MultivariateNormalTorch(200, cov=(np.eye(200) + 0.01).tolist(), device=CPU)      # gather limit: dim <= 128
+    with pytest.raises(ValueError):
+        td.SuperFunnelTorch(2, 2, [], [])                                                   # the reference's validation (:131-134)
+    sf = td.SuperFunnelTorch(2, 3, [torch.zeros(4, 3), torch.ones(5, 3)], [torch.zeros(4), torch.ones(5)], device=CPU)
+    assert sf.dim == 2 + 6 + 1 + 3 + 2 and sf.get_name() == "SuperFunnelTorch_J2_K3"
+    assert sf.pack().numel() == _lib.PARAM_HEADER + 9 * 5 and sf.pack()[9] == 9
 
 
 def test_proposal_plugins_match_reference_scales_and_errors():
@@ -200,5 +206,5 @@ def test_experiment_target_factory_matches_reference_defaults():
     assert get_target_distribution("ThreeMixtureScaled", 4, device="cpu").get_name() == "ThreeMixtureTorchScaled"
     with pytest.raises(ValueError):
         get_target_distribution("Nope", 3, device="cpu")
-    with pytest.raises(NotImplementedError):
-        get_target_distribution("SuperFunnel", 3, device="cpu")
+    sf = get_target_distribution("SuperFunnel", 3, device="cpu")       # synthetic data as experiment_RWM_GPU.py:95-120
+    assert sf.dim == 5 + 15 + 1 + 3 + 2 and sf.family_id == 12
