@@ -7,7 +7,7 @@ Same constructor arguments (same order), methods and attributes as the reference
 `swap_mode` ('reference' = what the reference really does on an accepted swap: copy k -> j, k unchanged,
 pt_rwm_gpu_optimized.py:50-59; 'exchange' = textbook PT), `math_mode`, `proposal_distribution` (Laplace /
 UniformRadius ladders, BASELINE config 4 -- an extension, the reference PT takes `var` only), `initial_states`,
-`chain_id_base`, `lanes_per_chain`.
+`chain_id_base` / `ladder_id_base`, `lanes_per_chain`.
 """
 from __future__ import annotations
 
@@ -57,7 +57,8 @@ class ParallelTemperingRWM_GPU_Optimized(MHAlgorithm):
                  proposal_distribution: ProposalDistribution = None,
                  initial_states=None,
                  chain_id_base: int = 0,
-                 lanes_per_chain: int = 0):
+                 lanes_per_chain: int = 0,
+                 ladder_id_base: Optional[int] = None):
         if not isinstance(target_dist, TorchTargetDistribution):
             raise TypeError("ParallelTemperingRWM_GPU_Optimized requires a TorchTargetDistribution.")
         self.num_ladders = int(num_ladders)
@@ -119,7 +120,9 @@ class ParallelTemperingRWM_GPU_Optimized(MHAlgorithm):
             raise ValueError("swap_mode must be 'reference' or 'exchange'")
         self.math_mode = math_mode
         self.seed = seed
-        self.chain_id_base = chain_id_base
+        # global id of this batch's first chain; `ladder_id_base` = the same in units of ladders (the ladder length is only
+        # known once the ladder is built, which is why shard helpers pass this one)
+        self.chain_id_base = chain_id_base if ladder_id_base is None else int(ladder_id_base) * self.num_chains
         self.lanes_per_chain = lanes_per_chain
         if initial_states is not None:
             x0 = np.asarray(initial_states, dtype=np.float64)

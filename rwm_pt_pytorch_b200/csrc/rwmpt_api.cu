@@ -291,17 +291,22 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   a.decisions = r->decisions; a.swap_dec = r->swap_decisions;
 
   if (r->samples) {
-    // staging region after the swap region: S rows per chain, S = 8 unless that needs more than ~64 KiB per CTA
+    // staging region after the swap region: S rows per chain (as many as keep the CTA's staging under ~32 KiB, several
+    // CTAs per SM), double-buffered for the bulk-copy flush of the fast kernels (RWMPT_BULK_STORE=0 restores the
+    // single-buffer vector flush for A/B measurements)
     const size_t swap_floats = (g.smem / sizeof(float) + 3) & ~(size_t)3;
-    int S = 16;  // rows staged per chain: as many as keep the CTA's staging region under ~24 KiB (several CTAs per SM)
-    while (S > 1 && (size_t)g.chains_per_cta * (((size_t)S * d + 3) & ~(size_t)3) * sizeof(float) > 24 * 1024) S >>= 1;
+    const char* eb = getenv("RWMPT_BULK_STORE");
+    const int bufs = (!ieee && !(eb && atoi(eb) == 0)) ? 2 : 1;
+    int S = 16;
+    while (S > 1 && (size_t)bufs * g.chains_per_cta * (((size_t)S * d + 3) & ~(size_t)3) * sizeof(float) > 32 * 1024) S >>= 1;
     const size_t st_stride = ((size_t)S * d + 3) & ~(size_t)3;
     const size_t lp_floats = ((size_t)g.chains_per_cta * S + 1) & ~(size_t)1;
     a.stage_rows = S;
+    a.stage_bufs = bufs;
     a.stage_off = (int)swap_floats;
     const uintptr_t p = reinterpret_cast<uintptr_t>(r->samples);
     a.stage_vw = (d % 4 == 0 && p % 16 == 0) ? 4 : ((d % 2 == 0 && p % 8 == 0) ? 2 : 1);
-    g.smem = (swap_floats + (size_t)g.chains_per_cta * st_stride + lp_floats) * sizeof(float);
+    g.smem = (swap_floats + (size_t)bufs * g.chains_per_cta * st_stride + lp_floats) * sizeof(float);
   }
   cudaError_t e = dispatch_mcmc(r->target.family, a, g, ieee, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "mcmc kernel launch");

@@ -52,6 +52,7 @@ struct KernelArgs {
   int stage_rows;  // rows per chain staged in shared memory before a coalesced flush
   int stage_off;   // offset (floats) of the staging region in dynamic shared memory
   int stage_vw;    // floats per vector store of the flush (4, 2 or 1)
+  int stage_bufs;  // 2: double-buffered staging, blocks leave through the bulk-copy engine (cp.async.bulk shared -> global)
   // balanced (time-sliced, ticketed) launch -- see mcmc_kernel; n_slices <= 1: plain launch, CTA b runs unit b
   int n_slices;
   int n_units;            // CTAs of the plain launch (= units of work)
@@ -156,6 +157,21 @@ __device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+
+// ---- bulk asynchronous copy shared::cta -> global (the TMA engine's 1-D form): one thread hands a contiguous, 16-byte
+// aligned block to the copy engine; the SM's load/store pipes never see the data again.
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until all but the N most recent bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// make this thread's generic-proxy writes to shared memory visible to the async proxy (the copy engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;

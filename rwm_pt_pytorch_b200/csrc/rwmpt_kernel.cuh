@@ -396,16 +396,34 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   // a.stage_vw floats (float4 when d % 4 == 0, float2 when d is even): one warp instruction writes 512 contiguous bytes.
   const int S = a.stage_rows;
   const int st_stride = (S * d + 3) & ~3;
-  float* st_base = smem + a.stage_off;                                  // [chains_per_cta][st_stride]
-  float* st_lp_base = st_base + (size_t)a.chains_per_cta * st_stride;    // [chains_per_cta][S]
-  float* st_x = st_base + (in_cta ? cl : 0) * st_stride;
+  // a.stage_bufs == 2: two staging buffers per chain; a full block leaves through the bulk-copy engine (one lane issues
+  // cp.async.bulk shared -> global for the chain's S*d*4 contiguous bytes) while the chain stages the next block in the other
+  // buffer -- no LDS / STG per lane, no scoreboard wait on the flush.  The engine needs 16-byte aligned source, destination
+  // and size: the FIRST block of a chain is cut short (`flush_at`) so that every later block starts on a 16-byte boundary
+  // of the sample buffer (d = 50: rows are 200 bytes, every second row is aligned); blocks that still miss the alignment
+  // (capacity clipping) take the vector path below.
+  const bool bulk = STORE && a.stage_bufs == 2;
+  const int nb = bulk ? 2 : 1;
+  float* st_base = smem + a.stage_off;                                        // [chains_per_cta][nb][st_stride]
+  float* st_lp_base = st_base + (size_t)a.chains_per_cta * nb * st_stride;     // [chains_per_cta][S]
+  float* st_x0 = st_base + (size_t)(in_cta ? cl : 0) * nb * st_stride;
+  float* st_x = st_x0;
+  int st_buf = 0;
   const bool stage_me = storing && valid;
   const bool store_each = has_samples && a.thin == 1 && s_first > a.store_start;  // every step of this run is retained
   int nbuf = 0;
   long long m_base = store_m;   // row index of staged row 0
+  int flush_at = S;
+  if (bulk && stage_me) {
+    const unsigned long long addr0 = (unsigned long long)(a.samples + (store_chain * a.sample_stride + m_base) * d);
+    const unsigned rb = 4u * (unsigned)d;
+    for (int f = 0; f < S; ++f)
+      if (((addr0 + (unsigned long long)f * rb) & 15ull) == 0ull) { flush_at = f == 0 ? S : f; break; }
+  }
   auto stage_flush = [&]() {
     // Each chain's W lanes copy their own chain's staged block: consecutive lanes write consecutive vectors, so every
     // 32-byte sector is written whole exactly once; no CTA barrier (a staging region is only touched by its own warp).
+    if (bulk) fence_async_smem();
     __syncwarp();
     long long rows = a.sample_rows - m_base;
     if (rows > nbuf) rows = nbuf;
@@ -413,7 +431,12 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
       const int n = (int)rows * d;
       const float* src = st_x;
       float* dst = a.samples + (store_chain * a.sample_stride + m_base) * d;
-      if (a.stage_vw == 4) {
+      if (bulk && (((unsigned long long)dst | (unsigned long long)(4 * n)) & 15ull) == 0ull) {
+        if (c.sub == 0) {
+          bulk_store_s2g(dst, src, 4u * (unsigned)n);
+          bulk_commit();
+        }
+      } else if (a.stage_vw == 4) {
         for (int v = c.sub; v < (n >> 2); v += W) reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(src)[v];
       } else if (a.stage_vw == 2) {
         for (int v = c.sub; v < (n >> 1); v += W) reinterpret_cast<float2*>(dst)[v] = reinterpret_cast<const float2*>(src)[v];
@@ -423,9 +446,16 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
       if (a.sample_logp != nullptr)
         for (int r = c.sub; r < (int)rows; r += W) a.sample_logp[store_chain * a.sample_stride + m_base + r] = st_lp_base[(size_t)cl * S + r];
     }
+    if (bulk) {
+      // switch buffers; the block that left from the other buffer one flush ago must have been read completely
+      st_buf ^= 1;
+      st_x = st_x0 + st_buf * st_stride;
+      if (stage_me && c.sub == 0) bulk_wait_read<1>();
+    }
     __syncwarp();
     m_base += nbuf;
     nbuf = 0;
+    flush_at = S;
   };
   auto stage_row = [&](const float (&xs)[E], float lpv) {
     if (stage_me) {
@@ -435,7 +465,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
       if (c.sub == 0) st_lp_base[(size_t)cl * S + nbuf] = lpv;
     }
     ++nbuf;
-    if (nbuf == S) stage_flush();
+    if (nbuf == flush_at) stage_flush();
   };
   const long long burn_t = a.burn_in > step_offset ? a.burn_in - step_offset : 0;  // local steps t >= burn_t count
 
@@ -850,6 +880,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
 
   // epilogue: staged samples, state, log-density, accumulators
   if (has_samples && nbuf > 0) stage_flush();
+  if (bulk && stage_me && c.sub == 0) bulk_wait_all<0>();   // every block has left shared memory AND landed before the CTA retires
   jump_d += (double)jump_f;
   n_acc += n_acc32;
   jump_d = group_sum_f64_w<WT>(jump_d, W);

@@ -113,3 +113,43 @@ def gather_samples(local: torch.Tensor, counts, dst: Optional[int] = None, group
         if rank != dst:
             return None
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+# ---- public multi-GPU entry points: one process per GPU (torchrun), no data-path collective ---------------------------
+def make_sharded(algorithm_cls, total_units: int, *args, group=None, **kwargs):
+    """Construct THIS rank's shard of a batched sampler: `total_units` independent chains (RandomWalkMH_GPU_Optimized) or
+    ladders (ParallelTemperingRWM_GPU_Optimized) are split into contiguous blocks over the ranks of `group`
+    (`shard_range`), the shard runs on the current CUDA device, and its Philox subsequences are the GLOBAL chain ids
+    (`chain_id_base` / `ladder_id_base`), so the pooled results are identical for 1, 2, 4 or 8 GPUs.  Without an
+    initialised process group the whole batch is one shard.  Returns (sampler, (first_unit, n_units))."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    first, count = shard_range(total_units, rank, world)
+    if count < 1:
+        raise ValueError(f"rank {rank} of {world} would get no unit of {total_units}")
+    is_pt = "ParallelTempering" in getattr(algorithm_cls, "__name__", "")
+    kw = dict(kwargs)
+    if is_pt:
+        kw["num_ladders"], kw["ladder_id_base"] = count, first
+    else:
+        kw["num_chains"], kw["chain_id_base"] = count, first
+    if "device" not in kw and torch.cuda.is_available():
+        kw["device"] = torch.device("cuda", torch.cuda.current_device())
+    return algorithm_cls(*args, **kw), (first, count)
+
+
+def finish_sharded(algo, shard, total_units: int, gather: bool = False, dst: Optional[int] = 0, group=None):
+    """After `generate_samples` on every rank: SUM all-reduce of the accumulators (-> pooled acceptance / ESJD / swap rates
+    of the whole job) and, with gather=True, the gather of the retained samples in global unit order (to `dst`, or to every
+    rank with dst=None).  Returns (pooled_summary dict, samples or None)."""
+    b = algo._batch
+    t = allreduce_statistics_tensor(local_statistics_tensor(algo), group=group)
+    total = statistics_from_tensor(t)
+    summary = pooled_summary(total, total["chain_steps"] / b.K)
+    samples = None
+    if gather and b.samples is not None:
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        per_unit = b.samples.shape[0] // shard[1]                        # stored chains per unit (K with store='all')
+        counts = [shard_range(total_units, r, world)[1] * per_unit for r in range(world)]
+        samples = gather_samples(b.samples[:, : b.rows_written()], counts, dst=dst, group=group)
+    return summary, samples

@@ -111,3 +111,48 @@ def test_device_side_statistics_match_the_host_side_ones(K):
     got = D.statistics_from_tensor(D.allreduce_statistics_tensor(D.local_statistics_tensor(algo)))
     for k in D.STAT_KEYS:
         assert got[k] == pytest.approx(want[k], rel=1e-12), k
+
+
+class ParallelTemperingFake:
+    """Records what make_sharded passes (class name contains 'ParallelTempering' like the real sampler)."""
+    def __init__(self, dim, **kw):
+        self.dim, self.kw = dim, kw
+
+
+class RWMFake(ParallelTemperingFake):
+    pass
+
+
+RWMFake.__name__ = "RandomWalkFake"
+
+
+def _shard_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pt, shard_pt = D.make_sharded(ParallelTemperingFake, 11, 20, device="cpu", swap_every=10)
+        rw, shard_rw = D.make_sharded(RWMFake, 4097, 20, device="cpu")
+        q.put((rank, pt.kw, shard_pt, rw.kw, shard_rw))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_make_sharded_hands_every_rank_its_block_and_global_ids():
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, pt0, s0, rw0, t0), (_, pt1, s1, rw1, t1) = res
+    assert (pt0["num_ladders"], pt0["ladder_id_base"], s0) == (6, 0, (0, 6)) and (pt1["num_ladders"], pt1["ladder_id_base"], s1) == (5, 6, (6, 5))
+    assert (rw0["num_chains"], rw0["chain_id_base"]) == (2049, 0) and (rw1["num_chains"], rw1["chain_id_base"]) == (2048, 2049)
+    assert pt0["swap_every"] == 10 and "chain_id_base" not in pt0 and "ladder_id_base" not in rw0
+    # single process: the whole batch is one shard
+    algo, shard = D.make_sharded(ParallelTemperingFake, 7, 3, device="cpu")
+    assert shard == (0, 7) and algo.kw["num_ladders"] == 7 and algo.kw["ladder_id_base"] == 0

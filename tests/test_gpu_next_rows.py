@@ -192,3 +192,30 @@ def test_benchmark_performance_schema_and_rates():
     sim.reset()
     chain = sim.generate_samples(progress_bar=False)
     assert len(chain) == 777
+
+
+def test_sharded_entry_points_equal_the_unsharded_run():
+    """distributed.make_sharded / finish_sharded (the public multi-GPU entry: one process per GPU) on one process, and two
+    hand-made shards with the ids make_sharded would assign: pooled statistics and gathered cold chains equal the single
+    batch bit for bit (Philox subsequence = global chain id)."""
+    _cuda()
+    from rwm_pt_pytorch_b200 import distributed as D
+    from rwm_pt_pytorch_b200.algorithms import ParallelTemperingRWM_GPU_Optimized as PT
+    from rwm_pt_pytorch_b200.target_distributions import RoughCarpetDistributionTorch
+    t = RoughCarpetDistributionTorch(20, device="cuda")
+    kw = dict(geom_temp_spacing=True, swap_every=10, burn_in=50, store="cold", seed=9, swap_mode="reference")
+    whole, shard = D.make_sharded(PT, 12, 20, 0.9, t, **kw)
+    assert shard == (0, 12) and whole.num_ladders == 12
+    whole.generate_samples(600)
+    summary, samples = D.finish_sharded(whole, shard, 12, gather=True)
+    parts = []
+    for first, count in ((0, 7), (7, 5)):
+        a = PT(20, 0.9, t, num_ladders=count, ladder_id_base=first, device="cuda", **kw)
+        a.generate_samples(600)
+        parts.append(a)
+    both = torch.cat([p._batch.samples[:, :p._batch.rows_written()] for p in parts], dim=0)
+    assert torch.equal(both, samples)
+    acc = sum(int(p._batch.accept_count.sum()) for p in parts)
+    assert summary["acceptance_rate"] == pytest.approx(acc / (12 * 8 * 600), rel=1e-12)
+    sw = sum(int(p.num_swap_acceptances) for p in parts) / sum(int(p.num_swap_attempts) for p in parts)
+    assert summary["swap_acceptance_rate"] == pytest.approx(sw, rel=1e-12)
