@@ -74,7 +74,7 @@ enum { RWMPT_MATH_FAST = 0, RWMPT_MATH_IEEE = 1 };
 enum { RWMPT_STORE_NONE = 0, RWMPT_STORE_COLD = 1, RWMPT_STORE_ALL = 2 };
 /* AUTO: balanced when a plain launch would load the SMs' warp schedulers unevenly (few warps per scheduler);
    PLAIN: one CTA per unit for the whole run; BALANCED: SM-sized grid, time-sliced units handed out by ticket. */
-enum { RWMPT_SCHEDULE_AUTO = 0, RWMPT_SCHEDULE_PLAIN = 1, RWMPT_SCHEDULE_BALANCED = 2 };
+enum { RWMPT_SCHEDULE_AUTO = 0, RWMPT_SCHEDULE_PLAIN = 1, RWMPT_SCHEDULE_BALANCED = 2, RWMPT_SCHEDULE_SPECIALISED = 3 };
 
 typedef struct {
   int32_t family;      /* RWMPT_T_*                                  */

@@ -414,11 +414,17 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   int nbuf = 0;
   long long m_base = store_m;   // row index of staged row 0
   int flush_at = S;
-  if (bulk && stage_me) {
-    const unsigned long long addr0 = (unsigned long long)(a.samples + (store_chain * a.sample_stride + m_base) * d);
-    const unsigned rb = 4u * (unsigned)d;
-    for (int f = 0; f < S; ++f)
-      if (((addr0 + (unsigned long long)f * rb) & 15ull) == 0ull) { flush_at = f == 0 ? S : f; break; }
+  if (bulk) {
+    if (stage_me) {
+      const unsigned long long addr0 = (unsigned long long)(a.samples + (store_chain * a.sample_stride + m_base) * d);
+      const unsigned rb = 4u * (unsigned)d;
+      for (int f = 0; f < S; ++f)
+        if (((addr0 + (unsigned long long)f * rb) & 15ull) == 0ull) { flush_at = f == 0 ? S : f; break; }
+    }
+    // the flush holds warp barriers, so every chain of a warp flushes at the same steps: the warp follows its first storing
+    // chain (chains whose buffer rows have the other alignment phase -- odd sample_stride with d = 50 -- keep the vector path)
+    const unsigned who = __ballot_sync(kFull, stage_me);
+    flush_at = __shfl_sync(kFull, flush_at, who ? __ffs(who) - 1 : 0);
   }
   auto stage_flush = [&]() {
     // Each chain's W lanes copy their own chain's staged block: consecutive lanes write consecutive vectors, so every

@@ -1,0 +1,247 @@
+// rwmpt_spec.cuh -- warp-specialised PT-RWM kernel for the FEW-LADDERS regime (strong scaling: BASELINE config 3's 1024
+// ladders sharded over 8 GPUs leave 128 ladders = 128 warps on a GPU with 592 warp schedulers).
+//
+// There the fused kernel is bound by the latency of ONE warp: a ladder-step is ~211 dependent-ish instructions, 60 % of
+// them randomness (Philox rounds, Box-Muller) that does not depend on the chain at all, and three of four schedulers idle.
+// Here a ladder is a CTA of two warps on two schedulers:
+//   * the PRODUCER warp draws the Philox words of a chunk of step pairs and turns them into scaled increments, log-uniforms
+//     and spare swap words -- exactly the words and transforms of mcmc_kernel (PhiloxPairGen, pair_transform), lane for lane --
+//     and leaves them in a shared-memory ring (one float4-interleaved slot per lane and pair);
+//   * the CONSUMER warp reads its lanes' slots and does nothing but propose / evaluate / accept / sweep.
+// Hand-over is by named barriers (bar.sync / bar.arrive on a full / empty pair per ring buffer): no CTA-wide barrier, no
+// polling.  A chunk ends where a sweep is due, so the consumer sweeps (warp shuffles, as in mcmc_kernel) while the producer
+// is already filling the other buffer.
+//
+// Results are those of mcmc_kernel: same Philox counters, same arithmetic, so states, log-densities, acceptance and swap
+// counters are bit-identical and the squared-jump sums agree to the grouping of their fp32 partial sums
+// (tests/test_gpu_parity.py::test_specialised_few_ladders_kernel_equals_fused_kernel).  The kernel takes only the regular part
+// of a run -- an even number of steps from an even offset, all on one side of the burn-in boundary, swap_every even, a
+// ladder that fills exactly one warp, accumulators only; the host (rwmpt_api.cu) runs the edges through mcmc_kernel, which
+// is resumable by construction.
+#pragma once
+
+#include "rwmpt_kernel.cuh"
+
+namespace rwmpt {
+
+constexpr int kSpecChunk = 8;    // pairs of steps per ring buffer (a chunk also ends where a sweep is due)
+constexpr int kSpecSlotF4 = 4;   // float4 per lane and pair: 2 x 5 increments, 2 log-uniforms, 2 spare words (14 of 16 words)
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Shared chunk arithmetic of the two roles: pairs in the next chunk given the pairs left and the pairs up to and including the
+// one the next sweep follows (`sw`, 0x7fffffff when the launch has no sweeps).
+__device__ __forceinline__ int spec_chunk_len(long long left, int sw) {
+  const int m = left < kSpecChunk ? (int)left : kSpecChunk;
+  return m < sw ? m : sw;
+}
+
+template <template <int, bool> class Target, int E, int WT, int PF>
+__global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
+  static_assert(2 * E + 4 <= 4 * kSpecSlotF4, "ring slot too small");
+  constexpr bool IEEE = false;
+  using M = Mth<IEEE>;
+  __shared__ float4 ring[2][kSpecChunk][kSpecSlotF4][32];   // [buffer][pair][word group][lane]: conflict-free LDS.128 / STS.128
+
+  const int K = a.K, d = a.dim;
+  const int lane = (int)threadIdx.x & 31;
+  const int role = (int)threadIdx.x >> 5;                   // 0: consumer (steps), 1: producer (randomness)
+  CtxT<WT, true> c;
+  c.P = a.P; c.d = d; c.W = WT;
+  c.sub = lane % WT;
+  c.base = c.sub * E;
+  c.lane = lane;
+  c.leader = lane & ~(WT - 1);
+  const long long ladder = blockIdx.x;
+  const int temp = lane / WT;
+  const long long chain = ladder * K + temp;
+  const unsigned long long chain_gid = (unsigned long long)(a.chain_id_base + chain);
+
+  const unsigned long long pair0 = (unsigned long long)a.step_offset >> 1;      // step_offset is even
+  const long long n_pairs = a.n_steps >> 1;                                      // n_steps is even
+  const bool post = a.step_offset >= a.burn_in;                                  // the whole launch is on one side of burn-in
+  const bool sweeps = post && K > 1;
+  const int half_se = a.swap_every >> 1;                                         // swap_every is even
+  // pairs up to and including the pair the first sweep follows: sweeps follow global steps s = m * swap_every > burn_in
+  int sw0 = 0x7fffffff;
+  if (sweeps) {
+    const long long s_first = a.step_offset + 1;
+    long long nxt = ((s_first + a.swap_every - 1) / a.swap_every) * a.swap_every;
+    if (nxt <= a.burn_in) nxt = (a.burn_in / a.swap_every + 1) * a.swap_every;
+    const long long pairs_to = (nxt - a.step_offset) >> 1;                       // nxt and step_offset are even
+    sw0 = pairs_to < 0x7fffffff ? (int)pairs_to : 0x7fffffff;
+  }
+
+  if (role == 1) {
+    // ------------------------------------------------ producer ------------------------------------------------
+    const float scale = a.prop_scale ? a.prop_scale[chain] : 1.0f;
+    float dscale[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) dscale[e] = a.prop_dim_scale ? a.prop_dim_scale[c.base + e] : 1.0f;
+    PhiloxPairGen<PairWords<E, PF>::NC> gen;
+    unsigned long long pair = pair0;
+    gen.init(a.rk, c.sub, pair, chain_gid);
+    long long left = n_pairs;
+    int sw = sw0, buf = 0;
+    long long chunk_no = 0;
+    while (left > 0) {
+      const int len = spec_chunk_len(left, sw);
+      if (chunk_no >= 2) named_bar_sync(2 + buf, 64);                            // buffer `buf` has been consumed
+      for (int p = 0; p < len; ++p) {
+        const unsigned long long pr = pair + (unsigned)p;
+        if ((uint32_t)(pr >> 32) != gen.hi32) gen.init(a.rk, c.sub, pr, chain_gid);
+        uint32_t w[4 * PairWords<E, PF>::NC];
+        gen.gen(a.rk, (uint32_t)pr, w);
+        float iA[E], iB[E], uA, uB;
+        uint32_t sA, sB;
+        pair_transform<E, IEEE, PF>(a, c, w, iA, iB, uA, uB, sA, sB, scale, dscale);
+        float v[4 * kSpecSlotF4];
+#pragma unroll
+        for (int q = 0; q < 4 * kSpecSlotF4; ++q) v[q] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) { v[e] = iA[e]; v[E + e] = iB[e]; }
+        v[2 * E] = uA; v[2 * E + 1] = uB;
+        v[2 * E + 2] = __uint_as_float(sA); v[2 * E + 3] = __uint_as_float(sB);
+#pragma unroll
+        for (int g = 0; g < kSpecSlotF4; ++g) ring[buf][p][g][lane] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
+      named_bar_arrive(buf, 64);                                                  // buffer `buf` is full
+      pair += (unsigned)len; left -= len;
+      if (sweeps) sw -= len;
+      if (sw == 0) sw = half_se;
+      buf ^= 1;
+      ++chunk_no;
+    }
+    // match the consumer's last "empty" arrivals so that no barrier is left half-armed when the CTA retires
+    if (chunk_no >= 2) named_bar_sync(2 + buf, 64);
+    if (chunk_no >= 1) named_bar_sync(2 + (buf ^ 1), 64);
+    return;
+  }
+
+  // -------------------------------------------------- consumer --------------------------------------------------
+  Target<E, IEEE> tgt;
+  tgt.init(c);
+  float x[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) x[e] = a.state[chain * d + c.base + e];
+  float lp = a.logp[chain];
+  const float beta = a.beta[chain];
+  const float beta_next = __shfl_down_sync(kFull, beta, WT);
+  const bool lead = c.sub == 0;
+  unsigned long long n_acc = 0, n_swap_acc = 0, last_attempt = 0;
+  double jump_d = 0.0;
+  long long round_local = 0;
+
+  // one Metropolis step on the lane's coordinates: the arithmetic of mcmc_unit's plain_step (packed fp32, EXACT mapping)
+  auto step = [&](const float (&inc)[E], const float u, float (&xo)[E], float& jadd, float& jf, unsigned& cnt) {
+    float prop[E];
+    float j2;
+    f32x2_t j2p = pack2(0.0f, 0.0f);
+#pragma unroll
+    for (int e = 0; e + 1 < E; e += 2) {
+      const f32x2_t i2 = pack2(inc[e], inc[e + 1]);
+      unpack2(add2(pack2(x[e], x[e + 1]), i2), prop[e], prop[e + 1]);
+      j2p = fma2(i2, i2, j2p);
+    }
+    float ja, jb;
+    unpack2(j2p, ja, jb);
+    j2 = ja + jb;
+    if constexpr (E & 1) {
+      prop[E - 1] = x[E - 1] + inc[E - 1];
+      j2 = fmaf(inc[E - 1], inc[E - 1], j2);
+    }
+    const float lpp = tgt.logp(prop, c);
+    const float lar = M::mul(beta, M::sub(lpp, lp));
+    const bool acc = mh_accept<IEEE>(lar, u);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      xo[e] = x[e];
+      x[e] = acc ? prop[e] : x[e];
+    }
+    jadd = acc ? j2 : 0.0f;
+    jf += jadd;
+    lp = acc ? lpp : lp;
+    cnt += acc ? 1u : 0u;
+  };
+
+  unsigned long long pair = pair0;
+  long long left = n_pairs;
+  int sw = sw0, buf = 0;
+  while (left > 0) {
+    const int len = spec_chunk_len(left, sw);
+    named_bar_sync(buf, 64);                                                      // wait until buffer `buf` is full
+    float jf = 0.0f;
+    unsigned cnt = 0;
+    float xo[E], jadd = 0.0f;
+    uint32_t spareB = 0u;
+    for (int p = 0; p < len; ++p) {
+      float v[4 * kSpecSlotF4];
+#pragma unroll
+      for (int g = 0; g < kSpecSlotF4; ++g) {
+        const float4 t = ring[buf][p][g][lane];
+        v[4 * g] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
+      }
+      float iA[E], iB[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) { iA[e] = v[e]; iB[e] = v[E + e]; }
+      spareB = __float_as_uint(v[2 * E + 3]);
+      step(iA, v[2 * E], xo, jadd, jf, cnt);
+      step(iB, v[2 * E + 1], xo, jadd, jf, cnt);
+    }
+    named_bar_arrive(2 + buf, 64);                                                // buffer `buf` may be refilled
+    pair += (unsigned)len; left -= len;
+    if (sweeps) sw -= len;
+    if (sw == 0) {
+      // adjacent-temperature sweep after the chunk's last step: reference semantics on the pre-sweep values, the pair's
+      // uniform is the spare accept word of the colder chain's second lane (mcmc_unit::sweep, warp-ladder form)
+      sw = half_se;
+      const unsigned long long round_g = (unsigned long long)(a.rounds_before + round_local);
+      const bool has_next = temp < K - 1;
+      const float us = u01_from_bits(__shfl_sync(kFull, spareB, c.leader + 1));
+      const float lp_n = __shfl_down_sync(kFull, lp, WT);
+      float xn[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) xn[e] = __shfl_down_sync(kFull, x[e], WT);
+      const bool ok = has_next && swap_accept<IEEE>(beta, beta_next, lp, lp_n, us);
+#pragma unroll
+      for (int e = 0; e < E; ++e) x[e] = ok ? xn[e] : x[e];
+      lp = ok ? lp_n : lp;
+      n_swap_acc += ok ? 1ull : 0ull;
+      last_attempt = ok ? round_g * (unsigned long long)(K - 1) + temp + 1 : last_attempt;
+      round_local++;
+      // the step's jump is chain[t+1] - chain[t] with the swap included (pt_rwm_gpu_optimized.py:772-789)
+      float j2 = 0.0f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float dx = M::sub(x[e], xo[e]);
+        j2 = fmaf(dx, dx, j2);
+      }
+      jf += ok ? j2 - jadd : 0.0f;
+    }
+    if (post) { jump_d += (double)jf; n_acc += cnt; }
+    buf ^= 1;
+  }
+
+  jump_d = group_sum_f64_w<WT>(jump_d, WT);
+#pragma unroll
+  for (int e = 0; e < E; ++e) a.state[chain * d + c.base + e] = x[e];
+  if (lead) {
+    a.logp[chain] = lp;
+    if (a.accept_count) a.accept_count[chain] += n_acc;
+    if (a.sq_jump_sum) a.sq_jump_sum[chain] += jump_d;
+    if (K > 1 && temp < K - 1 && a.swap_accepts) a.swap_accepts[ladder * (K - 1) + temp] += n_swap_acc;
+    if (K > 1 && a.swap_last_attempt && last_attempt > a.swap_last_attempt[chain]) a.swap_last_attempt[chain] = last_attempt;
+  }
+}
+
+template <template <int, bool> class Target, int E, int WT, int PF>
+cudaError_t launch_mcmc_spec(const KernelArgs& a, cudaStream_t st) {
+  mcmc_spec_kernel<Target, E, WT, PF><<<(unsigned)a.n_ladders, 64, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// defined in rwmpt_inst_rough_carpet.cu: the tuned BASELINE config 3 shape (RoughCarpet without scaling block, 5 x 4, Normal)
+cudaError_t launch_mcmc_spec_rough_carpet_c3(const KernelArgs& a, cudaStream_t st);
+
+}  // namespace rwmpt

@@ -786,6 +786,33 @@ def test_balanced_schedule_is_bit_identical_to_plain(store):
     torch.testing.assert_close(out[0][2], out[1][2], rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("burn,T1,T2", [(0, 2000, 0), (101, 1501, 700), (2000, 777, 1224), (50, 65, 3)])
+def test_specialised_few_ladders_kernel_equals_fused_kernel(burn, T1, T2):
+    """The warp-specialised kernel of the few-ladders regime (producer warp: Philox + Box-Muller into a shared-memory ring,
+    consumer warp: steps and sweeps; csrc/rwmpt_spec.cuh) against the fused kernel on BASELINE config 3's shape: states,
+    log-densities, acceptance / swap counters and refresh indices bit for bit, squared-jump sums to the grouping of their fp32
+    partial sums -- over odd burn-in boundaries, odd run lengths and a resumed second call (the host runs the edges
+    through the fused kernel)."""
+    dev = _cuda()
+    _, PT = _algs()
+    t = product_target("rough_carpet_d20")
+    runs = {}
+    for sched in (1, 3):                                      # RWMPT_SCHEDULE_PLAIN, RWMPT_SCHEDULE_SPECIALISED
+        algo = PT(20, 0.9, t, geom_temp_spacing=True, swap_every=10, burn_in=burn, device=dev, num_ladders=96, store="none",
+                  seed=4242, swap_mode="reference")
+        b = algo._batch
+        b.schedule = sched
+        b.run(T1)
+        if T2:
+            b.run(T2)
+        torch.cuda.synchronize()
+        runs[sched] = {k: getattr(b, k).cpu().numpy().copy() for k in ("state", "logp", "accept_count", "swap_accepts", "swap_last_attempt", "sq_jump_sum")}
+    for k in ("state", "logp", "accept_count", "swap_accepts", "swap_last_attempt"):
+        np.testing.assert_array_equal(runs[3][k], runs[1][k], err_msg=k)
+    np.testing.assert_allclose(runs[3]["sq_jump_sum"], runs[1]["sq_jump_sum"], rtol=2e-6, atol=1e-9)
+    assert runs[1]["accept_count"].sum() > 0 and (burn >= T1 + T2 or runs[1]["swap_accepts"].sum() > 0)
+
+
 def test_full_size_config3_properties():
     """BASELINE config 3 at its full width (1024 ladders x 8 temperatures, RoughCarpet d=20, swap_every 10, burn-in 2000):
     size-independent properties instead of an oracle run -- (a) one launch == two resumed launches, (b) two shards of 512
