@@ -824,6 +824,29 @@ def main():
         ("" if args.also in ("default", "none") else args.also)
     if also and world == 1:
         line["also"] = {}
+        # the strong-scaling regime on one GPU: config 3 with the ladders one GPU holds when 1024 are sharded over 2 / 4 / 8
+        # GPUs (auto schedule = warp-specialised kernel below 3.5 ladders per SM) next to the fused kernel forced (schedule 1)
+        few = {}
+        for u in (512, 256, 128):
+            wf = dict(WORKLOADS["c3"], units=u, T=100_000)
+            row = {}
+            for tag, sched in (("auto", None), ("fused_kernel_forced", "1")):
+                old_env = os.environ.get("RWMPT_SCHEDULE")
+                if sched is None:
+                    os.environ.pop("RWMPT_SCHEDULE", None)
+                else:
+                    os.environ["RWMPT_SCHEDULE"] = sched
+                mf = measure(wf, "none", False, 3, 3)
+                row[tag] = mf["rate"]
+                if old_env is None:
+                    os.environ.pop("RWMPT_SCHEDULE", None)
+                else:
+                    os.environ["RWMPT_SCHEDULE"] = old_env
+                del mf
+            row["frac_of_1024_ladder_rate"] = row["auto"] / line["value"]
+            few[str(u)] = row
+        line["also"]["c3_few_ladders_per_gpu"] = {"unit": "chain-steps/s", "steps_per_launch": 100_000, "ladders": few,
+                                                   "note": "per-GPU rate at the shard sizes of strong scaling (1024 ladders over 2 / 4 / 8 GPUs)"}
         for name in also.split(","):
             w2 = dict(WORKLOADS[name])
             st2 = w2.get("store", "none")

@@ -315,11 +315,13 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   // Few ladders per GPU (strong scaling): the warp-specialised kernel (rwmpt_spec.cuh) takes the regular middle of the run,
   // mcmc_kernel the edges -- up to the first even step at or past burn-in, and an odd last step -- each launch resuming the
   // previous one exactly (state, log-density, accumulators and Philox offsets are all functions of step_offset).
-  // Auto: when two warps per ladder still fit the 4 x 148 schedulers; RWMPT_SCHEDULE_SPECIALISED forces it where eligible.
+  // Auto: up to 3.5 ladders per SM; RWMPT_SCHEDULE_SPECIALISED forces it where eligible.
   const bool spec_shape = !ieee && !test_mode && r->target.family == RWMPT_T_ROUGH_CARPET && a.target_plain && g.E == 5 && g.W == 4 &&
                           d == 20 && r->proposal_family == RWMPT_P_NORMAL && r->n_temps == 8 && (a.swap_every & 1) == 0 &&
                           r->swap_mode == RWMPT_SWAP_REFERENCE && !r->samples && r->n_ladders <= 2147483647LL;
-  const bool spec_want = r->schedule == RWMPT_SCHEDULE_SPECIALISED || (r->schedule == RWMPT_SCHEDULE_AUTO && g.sms > 0 && r->n_ladders * 2 <= 4LL * g.sms);
+  // measured (profiles/r2_specialised_kernel.txt): +40 % at 128-296 ladders per GPU, +8 % at 512, -24 % at 1024 where the
+  // producers compete with the consumers for issue slots
+  const bool spec_want = r->schedule == RWMPT_SCHEDULE_SPECIALISED || (r->schedule == RWMPT_SCHEDULE_AUTO && g.sms > 0 && r->n_ladders * 2 <= 7LL * g.sms);
   if (spec_shape && spec_want) {
     const int64_t O = r->step_offset, N = r->n_steps, B = r->burn_in;
     int64_t head = O >= B ? 0 : B - O;          // steps that end at burn-in ...

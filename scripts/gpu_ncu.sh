@@ -1,5 +1,6 @@
-# ncu capture of the hot kernel for one workload: bash scripts/gpu_ncu.sh <workload> <tag> [extra bench args]
-WL=${1:-c3}; TAG=${2:-r1}; shift 2
+# ncu --set full capture of one launch of a kernel (after the same command has run clean without the profiler):
+#   bash scripts/gpu_ncu.sh <tag> <kernel regex> <skip> -- <command ...>
+TAG=$1; KRE=$2; SKIP=$3; shift 4
 mkdir -p gpurun_out
-python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu --no-e2e --T 2000 "$@" > gpurun_out/plain_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:mcmc_kernel -s 3 -c 1 -o gpurun_out/prof_$TAG python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu --no-e2e --T 2000 "$@" > gpurun_out/ncu_$TAG.log 2>&1
+"$@" > gpurun_out/plain_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:$KRE -s $SKIP -c 1 -f -o gpurun_out/prof_$TAG "$@" > gpurun_out/ncu_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_$TAG.log

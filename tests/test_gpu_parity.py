@@ -810,7 +810,7 @@ def test_specialised_few_ladders_kernel_equals_fused_kernel(burn, T1, T2):
     for k in ("state", "logp", "accept_count", "swap_accepts", "swap_last_attempt"):
         np.testing.assert_array_equal(runs[3][k], runs[1][k], err_msg=k)
     np.testing.assert_allclose(runs[3]["sq_jump_sum"], runs[1]["sq_jump_sum"], rtol=2e-6, atol=1e-9)
-    assert runs[1]["accept_count"].sum() > 0 and (burn >= T1 + T2 or runs[1]["swap_accepts"].sum() > 0)
+    assert runs[1]["accept_count"].sum() > 0 and (burn + 10 >= T1 + T2 or runs[1]["swap_accepts"].sum() > 0)
 
 
 def test_full_size_config3_properties():
