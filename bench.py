@@ -540,7 +540,8 @@ def aux_kernel_rates(dev, hbm_peak):
 
 def roofline_block(name, wl, per_gpu_rate, peaks, default_shape):
     """t_min = max(F / P_fp32, S / P_sfu, bytes / BW_hbm) per chain-step; achieved = rate x the
-    bounding resource's algorithmic work per chain-step."""
+    bounding resource's algorithmic work per chain-step.  default_shape: the workload runs its default number of units and
+    storage mode, so the committed ncu capture (profiles/ncu_traffic.json) describes this launch."""
     fp32_tf, sfu_g, hbm_peak, have_file = peaks
     t_sfu = wl["S"] / (sfu_g * 1e9)
     t_fp = wl["F"] / (fp32_tf * 1e12)
@@ -562,8 +563,14 @@ def roofline_block(name, wl, per_gpu_rate, peaks, default_shape):
             tr = json.load(open(NCU_TRAFFIC_FILE)).get(name)
         except (OSError, ValueError):
             tr = None
-    roof["traffic"] = tr["bytes"] if tr else None      # ncu dram bytes per launch, next to the algorithmic bytes per launch
-    roof["traffic_source"] = tr["source"] if tr else None
+    # ncu dram bytes per launch (read + write), next to the algorithmic bytes per launch; captures of stored-trajectory
+    # workloads are taken at a shorter run and scale with the steps per launch, accumulator-only ones do not depend on it
+    if tr:
+        k = wl["T"] / tr["capture_steps_per_launch"] if tr.get("scales_with_steps") else 1.0
+        roof["traffic"] = tr["bytes"] * k
+        roof["traffic_source"] = tr["source"] + (f" (captured at {tr['capture_steps_per_launch']} steps per launch, scaled)" if k != 1.0 else "")
+    else:
+        roof["traffic"] = roof["traffic_source"] = None
     roof["algorithmic_bytes_per_launch"] = wl["bytes"] * wl["units"] * wl["K"] * wl["T"]
     roof["per_chain_step"] = {"F": wl["F"], "S": wl["S"], "stored_bytes": wl["bytes"]}
     roof["frac_sfu_measured"] = per_gpu_rate * wl["S"] / (sfu_g * 1e9)
@@ -762,7 +769,7 @@ def main():
     hbm_peak = float(peaks_json.get("hbm_gbs", 6650.0))
     peaks = (fp32_tf.value, sfu_g.value, hbm_peak, have_peaks)
     base = WORKLOADS[args.workload]
-    default_shape = wl["T"] == base["T"] and wl["units"] == base["units"] and store == base.get("store", "none")
+    default_shape = wl["units"] == base["units"] and store == base.get("store", "none")   # (the steps per launch may differ)
     per_gpu = m["rate"] / world
     roof = roofline_block(args.workload, wl, per_gpu, peaks, default_shape)
     roof["measured_peaks"] = {"fp32_tflops": fp32_tf.value, "sfu_gops": sfu_g.value, "hbm_gbs": hbm_peak}
@@ -853,7 +860,7 @@ def main():
             m2 = measure(w2, st2, False, max(2, min(args.steps, 5)), 3)
             row = {"workload": w2["desc"], "value": m2["rate"], "unit": "chain-steps/s", "ms_per_step": m2["ms_per_step"],
                    "steps_per_launch": w2["T"], "step_ms": m2["step_ms"], "geometry_E_W": list(m2["batch"].geometry()),
-                   "roofline": roofline_block(name, w2, m2["rate"], peaks, w2["T"] == WORKLOADS[name]["T"]),
+                   "roofline": roofline_block(name, w2, m2["rate"], peaks, True),
                    "acceptance_rate": float(m2["batch"].accept_count.sum().item()) / max(m2["batch"].post_burn_in_steps() * m2["batch"].n_chains, 1)}
             if m2["note"]:
                 row["note"] = m2["note"]

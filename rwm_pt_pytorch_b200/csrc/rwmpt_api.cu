@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(256) esjd_moved_kernel(const float* __restrict
     const int r = lane / vpr, vec = lane - r * vpr;
     const bool lane_on = lane < R * vpr;
     const unsigned row_mask = vpr == 32 ? 0xffffffffu : ((1u << vpr) - 1u);
-    constexpr int U = 4;                                           // passes in flight
+    constexpr int U = 4;                                           // passes in flight (8 and a loop-free row count measured slower)
     for (long long j0 = lo + (long long)warp * R * U; j0 < hi; j0 += (long long)n_warps * R * U) {
       V c[U], p[U];
       bool on[U];

@@ -21,20 +21,25 @@ template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, b
 cudaError_t launch_mcmc_store(const KernelArgs& a_in, const LaunchGeom& g, cudaStream_t st);
 
 // Fast (non-test) kernels exist twice: with and without the retained-sample path, so that the accumulators-only kernels
-// do not depend on the store code.  Measured on one box (profiles/r1i_store_split_ab.txt): C2 (EvenRosenbrock) gains 15 %
-// from its store-free instantiation, C5 / C4 are unchanged, and ptxas schedules RoughCarpet's store-free instantiation 5 %
-// worse than the combined kernel -- that family keeps the single combined kernel (SplitStore<...>::value = false).
+// do not depend on the store code.  Measured: C2 (EvenRosenbrock) gains 15 % from its store-free instantiation, C5 / C4 are
+// unchanged (profiles/r1i_store_split_ab.txt); RoughCarpet kept a single combined kernel in round 1 (its store-free
+// instantiation scheduled 5 % worse then) -- with the double-buffered bulk-copy flush in the store path the store-free
+// instantiation is the faster one (2.405e10 vs 2.367e10 on C3, profiles/r2_variant_ab.txt), so every family is split now.
+// -DRWMPT_SPLIT_RC=0 restores the combined RoughCarpet kernel for A/B measurements.
 template <template <int, bool> class Target>
 struct SplitStore {
   static constexpr bool value = true;
 };
+#ifndef RWMPT_SPLIT_RC
+#define RWMPT_SPLIT_RC 1
+#endif
 template <>
 struct SplitStore<RoughCarpet> {
-  static constexpr bool value = false;
+  static constexpr bool value = RWMPT_SPLIT_RC != 0;
 };
 template <>
 struct SplitStore<RoughCarpetPlain> {
-  static constexpr bool value = false;
+  static constexpr bool value = RWMPT_SPLIT_RC != 0;
 };
 
 template <template <int, bool> class Target, int E, bool IEEE, int WT, int PF, bool EXACT, bool TEST, int VARIANT = 0>

@@ -16,7 +16,11 @@ try:
     print("C3", d["value"], d["roofline"]["frac"], "e2e", d.get("e2e", {}).get("value"), "clocks", d["clocks"])
     print("cpu_baseline", d.get("cpu_baseline", {}).get("value"), d.get("cpu_baseline", {}).get("kind"), "torch", {k: v.get("chain_steps_per_s") for k, v in d.get("reference_torch", {}).items() if isinstance(v, dict)})
     for k, v in d.get("also", {}).items():
-        print(k, v["value"], v["roofline"]["bound"], round(v["roofline"]["frac"], 4), "e2e", v.get("e2e", {}).get("value"), v.get("note"))
+        if "value" in v:
+            print(k, v["value"], v["roofline"]["bound"], round(v["roofline"]["frac"], 4), "e2e", v.get("e2e", {}).get("value"), v.get("note"))
+        else:
+            print(k, json.dumps(v.get("ladders")))
+    print("aux", {k: (v.get("flat", {}).get("frac_of_hbm_peak"), v.get("with_moved_count", {}).get("frac_of_hbm_peak")) if "flat" in v else v.get("frac_of_hbm_peak") for k, v in d.get("aux_kernels", {}).items()})
 except Exception as e:
     print("bench parse failed", e)
 PY
