@@ -2,7 +2,6 @@
 // plus the tuned (compile-time lanes-per-chain / proposal family) variants used by the BASELINE workloads.
 #include "rwmpt_launch.cuh"
 #define TUNED_LIST(cls)                                                                              \
-  RWMPT_TUNED_CASE_V(cls, 5, 2, 0, 2) RWMPT_TUNED_CASE_V(cls, 5, 4, 0, 2) RWMPT_TUNED_CASE_V(cls, 8, 4, 0, 2) \
   RWMPT_TUNED_CASE(cls, 5, 2, 0) RWMPT_TUNED_CASE(cls, 5, 4, 0) RWMPT_TUNED_CASE(cls, 8, 4, 0)
 RWMPT_DEFINE_TUNED(rwmpt::EvenRosenbrock, TUNED_LIST)
 RWMPT_DEFINE_FAMILY(even_rosenbrock, EvenRosenbrock)
