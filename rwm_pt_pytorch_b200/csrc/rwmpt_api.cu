@@ -323,6 +323,9 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   // producers compete with the consumers for issue slots
   const bool spec_want = r->schedule == RWMPT_SCHEDULE_SPECIALISED || (r->schedule == RWMPT_SCHEDULE_AUTO && g.sms > 0 && r->n_ladders * 2 <= 7LL * g.sms);
   if (spec_shape && spec_want) {
+    // consumer lanes per chain of the specialised kernel (RWMPT_SPEC_CW = 4 | 1 for A/B measurements)
+    const char* ecw = getenv("RWMPT_SPEC_CW");
+    const int spec_cw = ecw ? atoi(ecw) : 4;
     const int64_t O = r->step_offset, N = r->n_steps, B = r->burn_in;
     int64_t head = O >= B ? 0 : B - O;          // steps that end at burn-in ...
     if ((O + head) & 1) ++head;                 // ... or one later, so that the middle starts on an even step
@@ -336,7 +339,7 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
         s.step_offset = segs[k][0];
         s.n_steps = segs[k][1];
         s.rounds_before = count_rounds(0, s.step_offset, r->burn_in, a.swap_every);
-        cudaError_t e = (k == 1) ? launch_mcmc_spec_rough_carpet_c3(s, (cudaStream_t)stream)
+        cudaError_t e = (k == 1) ? launch_mcmc_spec_rough_carpet_c3(s, spec_cw, (cudaStream_t)stream)
                                  : dispatch_mcmc(r->target.family, s, g, ieee, (cudaStream_t)stream);
         if (e != cudaSuccess) return cuda_fail(e, k == 1 ? "specialised mcmc kernel launch" : "mcmc kernel launch");
       }

@@ -8,7 +8,8 @@
 RWMPT_DEFINE_TUNED(rwmpt::RoughCarpet, TUNED_LIST)
 RWMPT_DEFINE_FAMILY(rough_carpet, RoughCarpet)
 namespace rwmpt {
-cudaError_t launch_mcmc_spec_rough_carpet_c3(const KernelArgs& a, cudaStream_t st) {
-  return launch_mcmc_spec<RoughCarpetPlain, 5, 4, RWMPT_P_NORMAL>(a, st);
+cudaError_t launch_mcmc_spec_rough_carpet_c3(const KernelArgs& a, int consumer_lanes, cudaStream_t st) {
+  if (consumer_lanes == 1) return launch_mcmc_spec<RoughCarpetPlain, 5, 4, RWMPT_P_NORMAL, 1>(a, st);
+  return launch_mcmc_spec<RoughCarpetPlain, 5, 4, RWMPT_P_NORMAL, 4>(a, st);
 }
 }  // namespace rwmpt

@@ -37,9 +37,15 @@ __device__ __forceinline__ int spec_chunk_len(long long left, int sw) {
   return m < sw ? m : sw;
 }
 
-template <template <int, bool> class Target, int E, int WT, int PF>
+// CW = consumer lanes per chain: WT (the consumer keeps the fused kernel's lane mapping) or 1 (ONE consumer thread per chain: it
+// holds all E*WT coordinates, evaluates the WT lane partials of the density itself -- independent instruction streams instead
+// of a shuffle butterfly -- and adds them in the butterfly's order, so the log-density is bit-identical; 8 of the consumer
+// warp's lanes work, which costs nothing where the machine is three-quarters empty anyway).
+template <template <int, bool> class Target, int E, int WT, int PF, int CW>
 __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
   static_assert(2 * E + 4 <= 4 * kSpecSlotF4, "ring slot too small");
+  static_assert(CW == WT || CW == 1, "consumer lanes per chain: WT or 1");
+  static_assert(CW == WT || WT == 4, "the one-thread-per-chain consumer is written for four producer lanes per chain");
   constexpr bool IEEE = false;
   using M = Mth<IEEE>;
   __shared__ float4 ring[2][kSpecChunk][kSpecSlotF4][32];   // [buffer][pair][word group][lane]: conflict-free LDS.128 / STS.128
@@ -103,8 +109,11 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
         for (int e = 0; e < E; ++e) { v[e] = iA[e]; v[E + e] = iB[e]; }
         v[2 * E] = uA; v[2 * E + 1] = uB;
         v[2 * E + 2] = __uint_as_float(sA); v[2 * E + 3] = __uint_as_float(sB);
+        // CW == WT: slot = producer lane (the consumer lane of the same index reads it back); CW == 1: slot = sub * 8 + chain, so
+        // that the consumer lanes (one per chain) read consecutive float4
+        const int slot = CW == 1 ? c.sub * (32 / WT) + temp : lane;
 #pragma unroll
-        for (int g = 0; g < kSpecSlotF4; ++g) ring[buf][p][g][lane] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        for (int g = 0; g < kSpecSlotF4; ++g) ring[buf][p][g][slot] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
       }
       named_bar_arrive(buf, 64);                                                  // buffer `buf` is full
       pair += (unsigned)len; left -= len;
@@ -120,6 +129,123 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
   }
 
   // -------------------------------------------------- consumer --------------------------------------------------
+  if constexpr (CW == 1) {
+    constexpr int ET = E * WT;                                  // all coordinates of a chain in one thread
+    const int kc = lane < K ? lane : K - 1;                     // lanes >= K shadow the hottest chain and never write
+    const bool active = lane < K;
+    const long long ch = ladder * K + kc;
+    Target<E, IEEE> tgt;                                        // the E-coordinate functor: evaluated WT times per density
+    tgt.init(c);
+    float x[ET];
+#pragma unroll
+    for (int i = 0; i < ET; ++i) x[i] = a.state[ch * d + i];
+    float lp = a.logp[ch];
+    const float beta = a.beta[ch];
+    const float beta_next = __shfl_down_sync(kFull, beta, 1);
+    unsigned long long n_acc = 0, n_swap_acc = 0, last_attempt = 0;
+    double jump_d = 0.0;
+    long long round_local = 0;
+    auto density = [&](const float (&y)[ET]) -> float {
+      float part[WT];
+#pragma unroll
+      for (int v = 0; v < WT; ++v) {
+        float seg[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) seg[e] = y[v * E + e];
+        part[v] = tgt.lane_part_packed(seg);
+      }
+      // group_sum_w<4>: xor 2 then xor 1, as seen from lane 0 -- every lane of the butterfly ends with the same bits
+      return __fadd_rn(__fadd_rn(part[0], part[2]), __fadd_rn(part[1], part[3])) + tgt.J;
+    };
+    auto step1 = [&](const float (&inc)[ET], const float u, float (&xo)[ET], float& jadd, float& jf, unsigned& cnt) {
+      float prop[ET];
+      float j2 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < ET; ++i) {
+        prop[i] = x[i] + inc[i];
+        j2 = fmaf(inc[i], inc[i], j2);
+      }
+      const float lpp = density(prop);
+      const float lar = M::mul(beta, M::sub(lpp, lp));
+      const bool acc = mh_accept<IEEE>(lar, u);
+#pragma unroll
+      for (int i = 0; i < ET; ++i) {
+        xo[i] = x[i];
+        x[i] = acc ? prop[i] : x[i];
+      }
+      jadd = acc ? j2 : 0.0f;
+      jf += jadd;
+      lp = acc ? lpp : lp;
+      cnt += acc ? 1u : 0u;
+    };
+    unsigned long long pair = pair0;
+    long long left = n_pairs;
+    int sw = sw0, buf = 0;
+    while (left > 0) {
+      const int len = spec_chunk_len(left, sw);
+      named_bar_sync(buf, 64);
+      float jf = 0.0f;
+      unsigned cnt = 0;
+      float xo[ET], jadd = 0.0f;
+      uint32_t spareB = 0u;
+      for (int p = 0; p < len; ++p) {
+        float iA[ET], iB[ET], uA = 0.0f, uB = 0.0f;
+#pragma unroll
+        for (int v = 0; v < WT; ++v) {
+          float w[4 * kSpecSlotF4];
+#pragma unroll
+          for (int g = 0; g < kSpecSlotF4; ++g) {
+            const float4 t = ring[buf][p][g][v * (32 / WT) + kc];
+            w[4 * g] = t.x; w[4 * g + 1] = t.y; w[4 * g + 2] = t.z; w[4 * g + 3] = t.w;
+          }
+#pragma unroll
+          for (int e = 0; e < E; ++e) { iA[v * E + e] = w[e]; iB[v * E + e] = w[E + e]; }
+          if (v == 0) { uA = w[2 * E]; uB = w[2 * E + 1]; }                 // the chain's log-uniforms (leader's words)
+          if (v == 1) spareB = __float_as_uint(w[2 * E + 3]);               // spare word of the chain's second lane
+        }
+        step1(iA, uA, xo, jadd, jf, cnt);
+        step1(iB, uB, xo, jadd, jf, cnt);
+      }
+      named_bar_arrive(2 + buf, 64);
+      pair += (unsigned)len; left -= len;
+      if (sweeps) sw -= len;
+      if (sw == 0) {
+        sw = half_se;
+        const unsigned long long round_g = (unsigned long long)(a.rounds_before + round_local);
+        const bool has_next = active && kc < K - 1;
+        const float us = u01_from_bits(spareB);
+        const float lp_n = __shfl_down_sync(kFull, lp, 1);
+        float xn[ET];
+#pragma unroll
+        for (int i = 0; i < ET; ++i) xn[i] = __shfl_down_sync(kFull, x[i], 1);
+        const bool ok = has_next && swap_accept<IEEE>(beta, beta_next, lp, lp_n, us);
+        float j2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < ET; ++i) {
+          x[i] = ok ? xn[i] : x[i];
+          const float dx = M::sub(x[i], xo[i]);
+          j2 = fmaf(dx, dx, j2);
+        }
+        lp = ok ? lp_n : lp;
+        n_swap_acc += ok ? 1ull : 0ull;
+        last_attempt = ok ? round_g * (unsigned long long)(K - 1) + kc + 1 : last_attempt;
+        round_local++;
+        jf += ok ? j2 - jadd : 0.0f;
+      }
+      if (post) { jump_d += (double)jf; n_acc += cnt; }
+      buf ^= 1;
+    }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < ET; ++i) a.state[ch * d + i] = x[i];
+      a.logp[ch] = lp;
+      if (a.accept_count) a.accept_count[ch] += n_acc;
+      if (a.sq_jump_sum) a.sq_jump_sum[ch] += jump_d;
+      if (K > 1 && kc < K - 1 && a.swap_accepts) a.swap_accepts[ladder * (K - 1) + kc] += n_swap_acc;
+      if (K > 1 && a.swap_last_attempt && last_attempt > a.swap_last_attempt[ch]) a.swap_last_attempt[ch] = last_attempt;
+    }
+    return;
+  }
   Target<E, IEEE> tgt;
   tgt.init(c);
   float x[E];
@@ -235,13 +361,14 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
   }
 }
 
-template <template <int, bool> class Target, int E, int WT, int PF>
+template <template <int, bool> class Target, int E, int WT, int PF, int CW>
 cudaError_t launch_mcmc_spec(const KernelArgs& a, cudaStream_t st) {
-  mcmc_spec_kernel<Target, E, WT, PF><<<(unsigned)a.n_ladders, 64, 0, st>>>(a);
+  mcmc_spec_kernel<Target, E, WT, PF, CW><<<(unsigned)a.n_ladders, 64, 0, st>>>(a);
   return cudaGetLastError();
 }
 
-// defined in rwmpt_inst_rough_carpet.cu: the tuned BASELINE config 3 shape (RoughCarpet without scaling block, 5 x 4, Normal)
-cudaError_t launch_mcmc_spec_rough_carpet_c3(const KernelArgs& a, cudaStream_t st);
+// defined in rwmpt_inst_rough_carpet.cu: the tuned BASELINE config 3 shape (RoughCarpet without scaling block, 5 x 4, Normal);
+// consumer_lanes = 4 (fused kernel's mapping) or 1 (one consumer thread per chain)
+cudaError_t launch_mcmc_spec_rough_carpet_c3(const KernelArgs& a, int consumer_lanes, cudaStream_t st);
 
 }  // namespace rwmpt

@@ -42,6 +42,65 @@ struct RoughCarpetT {
     }
   }
 
+#ifndef RWMPT_NO_F32X2
+  // Lane partial of the fast path for a mapping without padding (base-2 form, see logp): what one lane contributes before
+  // the butterfly over the chain's lanes.  Separate so that a kernel which holds several lanes' coordinates in ONE thread
+  // (rwmpt_spec.cuh, one thread per chain) evaluates exactly the same partials and adds them in the butterfly's order.
+  __device__ __forceinline__ float lane_part_packed(const float (&x)[E]) const {
+    // packed fp32: coordinates (e, e+1) share every FFMA2 / FADD2 / FMUL2; max and ex2 stay scalar
+    const f32x2_t B0 = pack2(b0, b0), B1 = pack2(b1, b1), B2 = pack2(b2, b2);
+    const f32x2_t C0 = pack2(c0, c0), C1 = pack2(c1, c1), C2 = pack2(c2, c2);
+    f32x2_t hs2 = pack2(0.0f, 0.0f), qs2 = pack2(0.0f, 0.0f), ps2 = pack2(1.0f, 1.0f);
+#pragma unroll
+    for (int e = 0; e + 1 < E; e += 2) {
+      f32x2_t xs2 = pack2(x[e], x[e + 1]);
+      if constexpr (SCALED) xs2 = mul2(xs2, pack2(s[e], s[e + 1]));
+      const f32x2_t l0 = fma2(B0, xs2, C0), l1 = fma2(B1, xs2, C1), l2 = fma2(B2, xs2, C2);
+      float l0a, l0b, l1a, l1b, l2a, l2b;
+      unpack2(l0, l0a, l0b); unpack2(l1, l1a, l1b); unpack2(l2, l2a, l2b);
+      const f32x2_t mx2 = pack2(fmaxf(fmaxf(l0a, l1a), l2a), fmaxf(fmaxf(l0b, l1b), l2b));
+      float d0a, d0b, d1a, d1b, d2a, d2b;
+      const f32x2_t d0 = sub2(l0, mx2), d1 = sub2(l1, mx2), d2 = sub2(l2, mx2);
+      unpack2(d0, d0a, d0b); unpack2(d1, d1a, d1b); unpack2(d2, d2a, d2b);
+#ifndef RWMPT_RC_EXP3
+      // the largest term is exactly 2^0: two ex2 (smallest and middle exponent) instead of three
+      const f32x2_t lo2 = pack2(fminf(fminf(d0a, d1a), d2a), fminf(fminf(d0b, d1b), d2b));
+      float mda, mdb, loa, lob;
+      unpack2(sub2(add2(add2(d0, d1), d2), lo2), mda, mdb);
+      unpack2(lo2, loa, lob);
+      const f32x2_t ss2 = add2(add2(pack2(1.0f, 1.0f), pack2(ex2_approx(mda), ex2_approx(mdb))),
+                               pack2(ex2_approx(loa), ex2_approx(lob)));
+#else
+      const f32x2_t ss2 = add2(add2(pack2(ex2_approx(d0a), ex2_approx(d0b)), pack2(ex2_approx(d1a), ex2_approx(d1b))),
+                               pack2(ex2_approx(d2a), ex2_approx(d2b)));
+#endif
+      qs2 = fma2(xs2, xs2, qs2);
+      hs2 = add2(hs2, mx2);
+      ps2 = mul2(ps2, ss2);
+    }
+    float hsa, hsb, qsa, qsb, psa, psb;
+    unpack2(hs2, hsa, hsb); unpack2(qs2, qsa, qsb); unpack2(ps2, psa, psb);
+    if constexpr (E & 1) {
+      const float xs = SCALED ? x[E - 1] * s[E - 1] : x[E - 1];
+      const float l0 = fmaf(b0, xs, c0), l1 = fmaf(b1, xs, c1), l2 = fmaf(b2, xs, c2);
+      const float mx = fmaxf(fmaxf(l0, l1), l2);
+#ifndef RWMPT_RC_EXP3
+      const float lo = fminf(fminf(l0, l1), l2);
+      const float mid = ((l0 + l1) + l2) - (mx + lo);
+      const float ss = (1.0f + ex2_approx(mid - mx)) + ex2_approx(lo - mx);
+#else
+      const float ss = (ex2_approx(l0 - mx) + ex2_approx(l1 - mx)) + ex2_approx(l2 - mx);
+#endif
+      qsa = fmaf(xs, xs, qsa);
+      hsa += mx;
+      psa *= ss;
+    }
+    const float hi = fmaf(-0.5f * kLog2e, qsa + qsb, hsa + hsb);
+    const float part = (hi + lg2_approx(psa * psb)) * kLn2;
+    return part;
+  }
+#endif
+
   template <class C>
   __device__ __forceinline__ float logp(const float (&x)[E], const C& c) const {
     if constexpr (IEEE) {
@@ -67,57 +126,7 @@ struct RoughCarpetT {
       // 2^0, so two ex2 (smallest and middle exponent) instead of three; -DRWMPT_RC_EXP3 restores the three-ex2 form.
 #ifndef RWMPT_NO_F32X2
       if constexpr (C::EXACT && E >= 2) {
-        // packed fp32: coordinates (e, e+1) share every FFMA2 / FADD2 / FMUL2; max and ex2 stay scalar
-        const f32x2_t B0 = pack2(b0, b0), B1 = pack2(b1, b1), B2 = pack2(b2, b2);
-        const f32x2_t C0 = pack2(c0, c0), C1 = pack2(c1, c1), C2 = pack2(c2, c2);
-        f32x2_t hs2 = pack2(0.0f, 0.0f), qs2 = pack2(0.0f, 0.0f), ps2 = pack2(1.0f, 1.0f);
-#pragma unroll
-        for (int e = 0; e + 1 < E; e += 2) {
-          f32x2_t xs2 = pack2(x[e], x[e + 1]);
-          if constexpr (SCALED) xs2 = mul2(xs2, pack2(s[e], s[e + 1]));
-          const f32x2_t l0 = fma2(B0, xs2, C0), l1 = fma2(B1, xs2, C1), l2 = fma2(B2, xs2, C2);
-          float l0a, l0b, l1a, l1b, l2a, l2b;
-          unpack2(l0, l0a, l0b); unpack2(l1, l1a, l1b); unpack2(l2, l2a, l2b);
-          const f32x2_t mx2 = pack2(fmaxf(fmaxf(l0a, l1a), l2a), fmaxf(fmaxf(l0b, l1b), l2b));
-          float d0a, d0b, d1a, d1b, d2a, d2b;
-          const f32x2_t d0 = sub2(l0, mx2), d1 = sub2(l1, mx2), d2 = sub2(l2, mx2);
-          unpack2(d0, d0a, d0b); unpack2(d1, d1a, d1b); unpack2(d2, d2a, d2b);
-#ifndef RWMPT_RC_EXP3
-          // the largest term is exactly 2^0: two ex2 (smallest and middle exponent) instead of three
-          const f32x2_t lo2 = pack2(fminf(fminf(d0a, d1a), d2a), fminf(fminf(d0b, d1b), d2b));
-          float mda, mdb, loa, lob;
-          unpack2(sub2(add2(add2(d0, d1), d2), lo2), mda, mdb);
-          unpack2(lo2, loa, lob);
-          const f32x2_t ss2 = add2(add2(pack2(1.0f, 1.0f), pack2(ex2_approx(mda), ex2_approx(mdb))),
-                                   pack2(ex2_approx(loa), ex2_approx(lob)));
-#else
-          const f32x2_t ss2 = add2(add2(pack2(ex2_approx(d0a), ex2_approx(d0b)), pack2(ex2_approx(d1a), ex2_approx(d1b))),
-                                   pack2(ex2_approx(d2a), ex2_approx(d2b)));
-#endif
-          qs2 = fma2(xs2, xs2, qs2);
-          hs2 = add2(hs2, mx2);
-          ps2 = mul2(ps2, ss2);
-        }
-        float hsa, hsb, qsa, qsb, psa, psb;
-        unpack2(hs2, hsa, hsb); unpack2(qs2, qsa, qsb); unpack2(ps2, psa, psb);
-        if constexpr (E & 1) {
-          const float xs = SCALED ? x[E - 1] * s[E - 1] : x[E - 1];
-          const float l0 = fmaf(b0, xs, c0), l1 = fmaf(b1, xs, c1), l2 = fmaf(b2, xs, c2);
-          const float mx = fmaxf(fmaxf(l0, l1), l2);
-#ifndef RWMPT_RC_EXP3
-          const float lo = fminf(fminf(l0, l1), l2);
-          const float mid = ((l0 + l1) + l2) - (mx + lo);
-          const float ss = (1.0f + ex2_approx(mid - mx)) + ex2_approx(lo - mx);
-#else
-          const float ss = (ex2_approx(l0 - mx) + ex2_approx(l1 - mx)) + ex2_approx(l2 - mx);
-#endif
-          qsa = fmaf(xs, xs, qsa);
-          hsa += mx;
-          psa *= ss;
-        }
-        const float hi = fmaf(-0.5f * kLog2e, qsa + qsb, hsa + hsb);
-        const float part = (hi + lg2_approx(psa * psb)) * kLn2;
-        return group_sum(part, c) + J;
+        return group_sum(lane_part_packed(x), c) + J;
       }
 #endif
       float hs[2] = {0.0f, 0.0f}, ps[2] = {1.0f, 1.0f}, qs[2] = {0.0f, 0.0f};

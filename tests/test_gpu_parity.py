@@ -786,8 +786,9 @@ def test_balanced_schedule_is_bit_identical_to_plain(store):
     torch.testing.assert_close(out[0][2], out[1][2], rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("consumer_lanes", [4, 1])
 @pytest.mark.parametrize("burn,T1,T2", [(0, 2000, 0), (101, 1501, 700), (2000, 777, 1224), (50, 65, 3)])
-def test_specialised_few_ladders_kernel_equals_fused_kernel(burn, T1, T2):
+def test_specialised_few_ladders_kernel_equals_fused_kernel(burn, T1, T2, consumer_lanes, monkeypatch):
     """The warp-specialised kernel of the few-ladders regime (producer warp: Philox + Box-Muller into a shared-memory ring,
     consumer warp: steps and sweeps; csrc/rwmpt_spec.cuh) against the fused kernel on BASELINE config 3's shape: states,
     log-densities, acceptance / swap counters and refresh indices bit for bit, squared-jump sums to the grouping of their fp32
@@ -796,6 +797,7 @@ def test_specialised_few_ladders_kernel_equals_fused_kernel(burn, T1, T2):
     dev = _cuda()
     _, PT = _algs()
     t = product_target("rough_carpet_d20")
+    monkeypatch.setenv("RWMPT_SPEC_CW", str(consumer_lanes))   # consumer mapping: the fused kernel's 4 lanes per chain, or 1 thread
     runs = {}
     for sched in (1, 3):                                      # RWMPT_SCHEDULE_PLAIN, RWMPT_SCHEDULE_SPECIALISED
         algo = PT(20, 0.9, t, geom_temp_spacing=True, swap_every=10, burn_in=burn, device=dev, num_ladders=96, store="none",
