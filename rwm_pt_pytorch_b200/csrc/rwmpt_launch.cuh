@@ -133,42 +133,47 @@ struct Tuned {
 };
 
 // generic variants: runtime lanes-per-chain and proposal family.  IEEE kernels carry the test mode (injection,
-// decision outputs); fast kernels do not.
+// decision outputs); fast kernels do not.  The two halves are separate function templates so that each family compiles as
+// TWO translation units (rwmpt_inst_<family>.cu: fast, rwmpt_inst_<family>_ieee.cu: parity mode) -- 28 units instead of 14
+// for the parallel build.
 template <template <int, bool> class Target>
-cudaError_t launch_mcmc_family(const KernelArgs& a, const LaunchGeom& g, bool ieee, cudaStream_t st) {
-  if (ieee) {
-    switch (g.E) {
+cudaError_t launch_mcmc_family_ieee(const KernelArgs& a, const LaunchGeom& g, cudaStream_t st) {
+  switch (g.E) {
 #define X(e) case e: return launch_mcmc_one<Target, e, true, 0, -1, false, true>(a, g, st);
-      RWMPT_IEEE_E_LIST(X)
+    RWMPT_IEEE_E_LIST(X)
 #undef X
-    }
-  } else {
-    cudaError_t e = Tuned<Target>::launch(a, g, st);
-    if (e != cudaErrorNotSupported) return e;
-    switch (g.E) {
-#define X(e) case e: return launch_mcmc_one<Target, e, false, 0, -1, false, false>(a, g, st);
-      RWMPT_FAST_E_LIST(X)
-#undef X
-    }
   }
   return cudaErrorInvalidValue;
 }
 
 template <template <int, bool> class Target>
-cudaError_t launch_logp_family(const float* P, int d, int E, int W, const float* x, long long n, float* out, bool ieee,
-                               cudaStream_t st) {
-  if (ieee) {
-    switch (E) {
+cudaError_t launch_mcmc_family_fast(const KernelArgs& a, const LaunchGeom& g, cudaStream_t st) {
+  cudaError_t e = Tuned<Target>::launch(a, g, st);
+  if (e != cudaErrorNotSupported) return e;
+  switch (g.E) {
+#define X(e) case e: return launch_mcmc_one<Target, e, false, 0, -1, false, false>(a, g, st);
+    RWMPT_FAST_E_LIST(X)
+#undef X
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <template <int, bool> class Target>
+cudaError_t launch_logp_family_ieee(const float* P, int d, int E, int W, const float* x, long long n, float* out, cudaStream_t st) {
+  switch (E) {
 #define X(e) case e: return launch_logp_one<Target, e, true>(P, d, W, x, n, out, st);
-      RWMPT_IEEE_E_LIST(X)
+    RWMPT_IEEE_E_LIST(X)
 #undef X
-    }
-  } else {
-    switch (E) {
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <template <int, bool> class Target>
+cudaError_t launch_logp_family_fast(const float* P, int d, int E, int W, const float* x, long long n, float* out, cudaStream_t st) {
+  switch (E) {
 #define X(e) case e: return launch_logp_one<Target, e, false>(P, d, W, x, n, out, st);
-      RWMPT_FAST_E_LIST(X)
+    RWMPT_FAST_E_LIST(X)
 #undef X
-    }
   }
   return cudaErrorInvalidValue;
 }
@@ -238,17 +243,33 @@ RWMPT_FAMILY_LIST(X)
 
 #define RWMPT_DEFINE_FAMILY(name, cls)                                                                        \
   namespace rwmpt {                                                                                           \
+  cudaError_t launch_mcmc_ieee_##name(const KernelArgs& a, const LaunchGeom& g, cudaStream_t st);             \
+  cudaError_t launch_logp_ieee_##name(const float* P, int d, int E, int W, const float* x, long long n,       \
+                                      float* out, cudaStream_t st);                                           \
   cudaError_t launch_mcmc_##name(const KernelArgs& a, const LaunchGeom& g, bool ieee, cudaStream_t st) {      \
-    return launch_mcmc_family<cls>(a, g, ieee, st);                                                           \
+    return ieee ? launch_mcmc_ieee_##name(a, g, st) : launch_mcmc_family_fast<cls>(a, g, st);                 \
   }                                                                                                           \
   cudaError_t launch_logp_##name(const float* P, int d, int E, int W, const float* x, long long n, float* out, \
                                  bool ieee, cudaStream_t st) {                                                \
-    return launch_logp_family<cls>(P, d, E, W, x, n, out, ieee, st);                                          \
+    return ieee ? launch_logp_ieee_##name(P, d, E, W, x, n, out, st)                                          \
+                : launch_logp_family_fast<cls>(P, d, E, W, x, n, out, st);                                    \
   }                                                                                                           \
   cudaError_t launch_swap_prob_##name(const float* P, int d, int E, int W, float bc, float bs, long long n,    \
                                       unsigned k0, unsigned k1, long long row_base, double* sum_out,          \
                                       cudaStream_t st) {                                                      \
     return launch_swap_prob_family<cls>(P, d, E, W, bc, bs, n, k0, k1, row_base, sum_out, st);                \
+  }                                                                                                           \
+  }
+
+// the parity-mode half of a family, in its own translation unit (rwmpt_inst_<family>_ieee.cu)
+#define RWMPT_DEFINE_FAMILY_IEEE(name, cls)                                                                   \
+  namespace rwmpt {                                                                                           \
+  cudaError_t launch_mcmc_ieee_##name(const KernelArgs& a, const LaunchGeom& g, cudaStream_t st) {            \
+    return launch_mcmc_family_ieee<cls>(a, g, st);                                                            \
+  }                                                                                                           \
+  cudaError_t launch_logp_ieee_##name(const float* P, int d, int E, int W, const float* x, long long n,       \
+                                      float* out, cudaStream_t st) {                                          \
+    return launch_logp_family_ieee<cls>(P, d, E, W, x, n, out, st);                                           \
   }                                                                                                           \
   }
 
