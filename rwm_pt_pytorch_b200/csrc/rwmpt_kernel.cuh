@@ -402,7 +402,15 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   // and size: the FIRST block of a chain is cut short (`flush_at`) so that every later block starts on a 16-byte boundary
   // of the sample buffer (d = 50: rows are 200 bytes, every second row is aligned); blocks that still miss the alignment
   // (capacity clipping) take the vector path below.
-  const bool bulk = STORE && a.stage_bufs == 2;
+  // RoughCarpet keeps the single-buffer vector flush AND a single combined (store + accumulators-only) kernel: with the
+  // bulk-copy code in it, ptxas schedules the accumulators-only loop of BASELINE config 3 -- the headline workload -- 1.7-3 %
+  // slower (2.455e10 vs 2.41e10 / 2.37e10, profiles/r2_variant_ab.txt).  -DRWMPT_RC_BULK=1 -DRWMPT_SPLIT_RC=1 for A/B.
+#ifdef RWMPT_RC_BULK
+  constexpr bool kBulkOk = true;
+#else
+  constexpr bool kBulkOk = !(std::is_same<Target<E, IEEE>, RoughCarpetT<E, IEEE, true>>::value || std::is_same<Target<E, IEEE>, RoughCarpetT<E, IEEE, false>>::value);
+#endif
+  const bool bulk = STORE && kBulkOk && a.stage_bufs == 2;
   const int nb = bulk ? 2 : 1;
   float* st_base = smem + a.stage_off;                                        // [chains_per_cta][nb][st_stride]
   float* st_lp_base = st_base + (size_t)a.chains_per_cta * nb * st_stride;     // [chains_per_cta][S]

@@ -22,16 +22,15 @@ cudaError_t launch_mcmc_store(const KernelArgs& a_in, const LaunchGeom& g, cudaS
 
 // Fast (non-test) kernels exist twice: with and without the retained-sample path, so that the accumulators-only kernels
 // do not depend on the store code.  Measured: C2 (EvenRosenbrock) gains 15 % from its store-free instantiation, C5 / C4 are
-// unchanged (profiles/r1i_store_split_ab.txt); RoughCarpet kept a single combined kernel in round 1 (its store-free
-// instantiation scheduled 5 % worse then) -- with the double-buffered bulk-copy flush in the store path the store-free
-// instantiation is the faster one (2.405e10 vs 2.367e10 on C3, profiles/r2_variant_ab.txt), so every family is split now.
-// -DRWMPT_SPLIT_RC=0 restores the combined RoughCarpet kernel for A/B measurements.
+// unchanged (profiles/r1i_store_split_ab.txt).  RoughCarpet keeps ONE combined kernel with the round-1 store path: its
+// store-free instantiation schedules 1.7 % worse than that (round 1: 5 %), and the combined kernel WITH the bulk-copy store
+// code 3 % worse (profiles/r2_variant_ab.txt).  -DRWMPT_SPLIT_RC=1 builds the store-free RoughCarpet instantiation for A/B.
 template <template <int, bool> class Target>
 struct SplitStore {
   static constexpr bool value = true;
 };
 #ifndef RWMPT_SPLIT_RC
-#define RWMPT_SPLIT_RC 1
+#define RWMPT_SPLIT_RC 0
 #endif
 template <>
 struct SplitStore<RoughCarpet> {
