@@ -15,6 +15,11 @@ namespace rwmpt {
 
 static thread_local char g_err[512] = "";
 
+// warp-specialised kernel for RWM (config 2): producers per consumer warp, and the auto rule's bound on the fused kernel's
+// warps per SM (set from measurements, profiles/r2_specialised_kernel.txt)
+constexpr int kSpecRwmProducers = 2;
+constexpr int kSpecRwmAutoWarpsPerSm = 0;   // 0: never automatically (RWMPT_SCHEDULE_SPECIALISED only) until measured
+
 // family name (RWMPT_FAMILY_LIST) -> enum of include/rwmpt.h
 #define RWMPT_FAMILY_ID_rough_carpet RWMPT_T_ROUGH_CARPET
 #define RWMPT_FAMILY_ID_three_mixture RWMPT_T_THREE_MIXTURE
@@ -312,20 +317,31 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
     a.stage_vw = (d % 4 == 0 && p % 16 == 0) ? 4 : ((d % 2 == 0 && p % 8 == 0) ? 2 : 1);
     g.smem = (swap_floats + (size_t)bufs * g.chains_per_cta * st_stride + lp_floats) * sizeof(float);
   }
-  // Few ladders per GPU (strong scaling): the warp-specialised kernel (rwmpt_spec.cuh) takes the regular middle of the run,
-  // mcmc_kernel the edges -- up to the first even step at or past burn-in, and an odd last step -- each launch resuming the
-  // previous one exactly (state, log-density, accumulators and Philox offsets are all functions of step_offset).
-  // Auto: up to 3.5 ladders per SM; RWMPT_SCHEDULE_SPECIALISED forces it where eligible.
-  const bool spec_shape = !ieee && !test_mode && r->target.family == RWMPT_T_ROUGH_CARPET && a.target_plain && g.E == 5 && g.W == 4 &&
-                          d == 20 && r->proposal_family == RWMPT_P_NORMAL && r->n_temps == 8 && (a.swap_every & 1) == 0 &&
-                          r->swap_mode == RWMPT_SWAP_REFERENCE && !r->samples && r->n_ladders <= 2147483647LL;
-  // measured (profiles/r2_specialised_kernel.txt): +40 % at 128-296 ladders per GPU, +8 % at 512, -24 % at 1024 where the
-  // producers compete with the consumers for issue slots
-  const bool spec_want = r->schedule == RWMPT_SCHEDULE_SPECIALISED || (r->schedule == RWMPT_SCHEDULE_AUTO && g.sms > 0 && r->n_ladders * 2 <= 7LL * g.sms);
-  if (spec_shape && spec_want) {
-    // consumer lanes per chain of the specialised kernel (RWMPT_SPEC_CW = 4 | 1 for A/B measurements)
+  // Few warps per GPU (strong scaling of config 3, config 2's 4096 chains): the warp-specialised kernel (rwmpt_spec.cuh) takes the
+  // regular middle of the run, mcmc_kernel the edges -- up to the first even step at or past burn-in, and an odd last step --
+  // each launch resuming the previous one exactly (state, log-density, accumulators and Philox offsets are all functions of
+  // step_offset).  Shapes: chains fill whole warps without padding (E * W == dim), Normal proposal, accumulators only; for a
+  // ladder: 8 temperatures x 4 lanes = one warp, swap_every even, the reference's swap semantics.
+  // Auto: PT up to 3.5 ladders per SM (measured: +40 % at 64-296 ladders per GPU, +8 % at 512, -24 % at 1024); RWM see below.
+  // RWMPT_SCHEDULE_SPECIALISED forces it where eligible; RWMPT_SPEC_CW / RWMPT_SPEC_NP choose the consumer mapping / producers.
+  const long long n_chains_all = r->n_ladders * r->n_temps;
+  const int cpw = 32 / g.W;
+  const bool spec_common = !ieee && !test_mode && !r->samples && r->proposal_family == RWMPT_P_NORMAL && g.E * g.W == d &&
+                           n_chains_all % cpw == 0 && n_chains_all / cpw <= 2147483647LL;
+  const bool spec_pt = spec_common && r->target.family == RWMPT_T_ROUGH_CARPET && a.target_plain && r->n_temps == 8 && g.W == 4 &&
+                       (a.swap_every & 1) == 0 && r->swap_mode == RWMPT_SWAP_REFERENCE;
+  const bool spec_rwm = spec_common && r->target.family == RWMPT_T_EVEN_ROSENBROCK && r->n_temps == 1 && g.E == 5 && (g.W == 4 || g.W == 2);
+  const long long fused_warps = n_chains_all / cpw;
+  bool spec_want = r->schedule == RWMPT_SCHEDULE_SPECIALISED;
+  if (r->schedule == RWMPT_SCHEDULE_AUTO && g.sms > 0) {
+    if (spec_pt) spec_want = fused_warps * 2 <= 7LL * g.sms;
+    if (spec_rwm) spec_want = fused_warps <= (long long)kSpecRwmAutoWarpsPerSm * g.sms;
+  }
+  if ((spec_pt || spec_rwm) && spec_want) {
     const char* ecw = getenv("RWMPT_SPEC_CW");
-    const int spec_cw = ecw ? atoi(ecw) : 4;
+    const char* enp = getenv("RWMPT_SPEC_NP");
+    const int spec_cw = ecw ? atoi(ecw) : g.W;
+    const int spec_np = enp ? atoi(enp) : (spec_rwm ? kSpecRwmProducers : 1);
     const int64_t O = r->step_offset, N = r->n_steps, B = r->burn_in;
     int64_t head = O >= B ? 0 : B - O;          // steps that end at burn-in ...
     if ((O + head) & 1) ++head;                 // ... or one later, so that the middle starts on an even step
@@ -339,8 +355,13 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
         s.step_offset = segs[k][0];
         s.n_steps = segs[k][1];
         s.rounds_before = count_rounds(0, s.step_offset, r->burn_in, a.swap_every);
-        cudaError_t e = (k == 1) ? launch_mcmc_spec_rough_carpet_c3(s, spec_cw, (cudaStream_t)stream)
-                                 : dispatch_mcmc(r->target.family, s, g, ieee, (cudaStream_t)stream);
+        cudaError_t e;
+        if (k == 1) {
+          e = spec_pt ? launch_spec_rough_carpet(s, g.E, g.W, spec_cw, spec_np, (cudaStream_t)stream)
+                      : launch_spec_even_rosenbrock(s, g.E, g.W, spec_cw, spec_np, (cudaStream_t)stream);
+        } else {
+          e = dispatch_mcmc(r->target.family, s, g, ieee, (cudaStream_t)stream);
+        }
         if (e != cudaSuccess) return cuda_fail(e, k == 1 ? "specialised mcmc kernel launch" : "mcmc kernel launch");
       }
       return RWMPT_OK;

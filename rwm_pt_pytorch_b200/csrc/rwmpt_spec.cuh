@@ -1,67 +1,79 @@
-// rwmpt_spec.cuh -- warp-specialised PT-RWM kernel for the FEW-LADDERS regime (strong scaling: BASELINE config 3's 1024
-// ladders sharded over 8 GPUs leave 128 ladders = 128 warps on a GPU with 592 warp schedulers).
+// rwmpt_spec.cuh -- warp-specialised RWM / PT-RWM kernel for the FEW-WARPS regime: BASELINE config 3 under strong scaling
+// (1024 ladders sharded over 8 GPUs leave 128 ladders = 128 warps on a GPU with 592 warp schedulers) and BASELINE config 2
+// (4096 chains of d = 20 are 512 warps).
 //
-// There the fused kernel is bound by the latency of ONE warp: a ladder-step is ~211 dependent-ish instructions, 60 % of
-// them randomness (Philox rounds, Box-Muller) that does not depend on the chain at all, and three of four schedulers idle.
-// Here a ladder is a CTA of two warps on two schedulers:
-//   * the PRODUCER warp draws the Philox words of a chunk of step pairs and turns them into scaled increments, log-uniforms
+// There the fused kernel is bound by the latency of ONE warp: a step is ~100-200 dependent-ish instructions, most of them
+// randomness (Philox rounds, Box-Muller) that does not depend on the chain at all, while schedulers idle.  Here a warp's worth
+// of chains (a whole ladder for PT) is a CTA of 1 + NP warps on as many schedulers:
+//   * the NP PRODUCER warps draw the Philox words of chunks of step pairs and turn them into scaled increments, log-uniforms
 //     and spare swap words -- exactly the words and transforms of mcmc_kernel (PhiloxPairGen, pair_transform), lane for lane --
-//     and leaves them in a shared-memory ring (one float4-interleaved slot per lane and pair);
+//     and leave them in a shared-memory ring (one float4-interleaved slot per lane and pair, two buffers per producer);
 //   * the CONSUMER warp reads its lanes' slots and does nothing but propose / evaluate / accept / sweep.
 // Hand-over is by named barriers (bar.sync / bar.arrive on a full / empty pair per ring buffer): no CTA-wide barrier, no
-// polling.  A chunk ends where a sweep is due, so the consumer sweeps (warp shuffles, as in mcmc_kernel) while the producer
-// is already filling the other buffer.
+// polling.  A chunk ends where a sweep is due, so the consumer sweeps (warp shuffles, as in mcmc_kernel) while the producers
+// are already filling other buffers.
 //
 // Results are those of mcmc_kernel: same Philox counters, same arithmetic, so states, log-densities, acceptance and swap
 // counters are bit-identical and the squared-jump sums agree to the grouping of their fp32 partial sums
-// (tests/test_gpu_parity.py::test_specialised_few_ladders_kernel_equals_fused_kernel).  The kernel takes only the regular part
-// of a run -- an even number of steps from an even offset, all on one side of the burn-in boundary, swap_every even, a
-// ladder that fills exactly one warp, accumulators only; the host (rwmpt_api.cu) runs the edges through mcmc_kernel, which
-// is resumable by construction.
+// (tests/test_gpu_parity.py::test_specialised_*).  The kernel takes only the regular part of a run -- an even number of steps
+// from an even offset, all on one side of the burn-in boundary, swap_every even, chains that fill whole warps without padding
+// (for PT: a ladder that fills exactly one warp), accumulators only; the host (rwmpt_api.cu) runs the edges through
+// mcmc_kernel, which is resumable by construction.
 #pragma once
 
 #include "rwmpt_kernel.cuh"
 
 namespace rwmpt {
 
-constexpr int kSpecChunk = 8;    // pairs of steps per ring buffer (a chunk also ends where a sweep is due)
-constexpr int kSpecSlotF4 = 4;   // float4 per lane and pair: 2 x 5 increments, 2 log-uniforms, 2 spare words (14 of 16 words)
-
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// Shared chunk arithmetic of the two roles: pairs in the next chunk given the pairs left and the pairs up to and including the
-// one the next sweep follows (`sw`, 0x7fffffff when the launch has no sweeps).
+// geometry of the ring: SLOT float4 per lane and pair (2E increments, 2 log-uniforms, 2 spare words), NB = 2 NP buffers of CH
+// pairs each, about 32 KiB in all
+template <int E, int NP>
+struct SpecRing {
+  static constexpr int SLOT = (2 * E + 4 + 3) / 4;
+  static constexpr int NB = 2 * NP;
+  static constexpr int CH_RAW = (32 * 1024) / (NB * SLOT * 512);
+  static constexpr int CH = CH_RAW < 1 ? 1 : (CH_RAW > 8 ? 8 : CH_RAW);
+};
+
+// Shared chunk arithmetic of all roles: pairs in the next chunk given the pairs left and the pairs up to and including the one
+// the next sweep follows (`sw`, 0x7fffffff when the launch has no sweeps).
+template <int CH>
 __device__ __forceinline__ int spec_chunk_len(long long left, int sw) {
-  const int m = left < kSpecChunk ? (int)left : kSpecChunk;
+  const int m = left < CH ? (int)left : CH;
   return m < sw ? m : sw;
 }
 
 // CW = consumer lanes per chain: WT (the consumer keeps the fused kernel's lane mapping) or 1 (ONE consumer thread per chain: it
 // holds all E*WT coordinates, evaluates the WT lane partials of the density itself -- independent instruction streams instead
-// of a shuffle butterfly -- and adds them in the butterfly's order, so the log-density is bit-identical; 8 of the consumer
-// warp's lanes work, which costs nothing where the machine is three-quarters empty anyway).
-template <template <int, bool> class Target, int E, int WT, int PF, int CW>
-__global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
-  static_assert(2 * E + 4 <= 4 * kSpecSlotF4, "ring slot too small");
+// of a shuffle butterfly -- and adds them in the butterfly's order, so the log-density is bit-identical; measured 2x slower
+// (issue-bound), kept as a knob for the RoughCarpet 5 x 4 shape).  NP = producer warps.
+template <template <int, bool> class Target, int E, int WT, int PF, int CW, int NP>
+__global__ void __launch_bounds__(32 * (1 + NP)) mcmc_spec_kernel(const KernelArgs a) {
+  using R = SpecRing<E, NP>;
+  constexpr int SLOT = R::SLOT, NB = R::NB, CH = R::CH;
+  constexpr int CPW = 32 / WT;                                // chains per warp
   static_assert(CW == WT || CW == 1, "consumer lanes per chain: WT or 1");
   static_assert(CW == WT || WT == 4, "the one-thread-per-chain consumer is written for four producer lanes per chain");
   constexpr bool IEEE = false;
   using M = Mth<IEEE>;
-  __shared__ float4 ring[2][kSpecChunk][kSpecSlotF4][32];   // [buffer][pair][word group][lane]: conflict-free LDS.128 / STS.128
+  __shared__ float4 ring[NB][CH][SLOT][32];                   // [buffer][pair][word group][slot]: conflict-free LDS.128 / STS.128
 
   const int K = a.K, d = a.dim;
   const int lane = (int)threadIdx.x & 31;
-  const int role = (int)threadIdx.x >> 5;                   // 0: consumer (steps), 1: producer (randomness)
+  const int role = (int)threadIdx.x >> 5;                   // 0: consumer (steps), 1 .. NP: producers (randomness)
   CtxT<WT, true> c;
   c.P = a.P; c.d = d; c.W = WT;
   c.sub = lane % WT;
   c.base = c.sub * E;
   c.lane = lane;
   c.leader = lane & ~(WT - 1);
-  const long long ladder = blockIdx.x;
-  const int temp = lane / WT;
-  const long long chain = ladder * K + temp;
+  const int cw = lane / WT;                                   // chain within the warp
+  const long long chain = (long long)blockIdx.x * CPW + cw;   // K > 1: the warp is one ladder (K == CPW), cw is the temperature
+  const long long ladder = chain / K;
+  const int temp = K > 1 ? cw : 0;
   const unsigned long long chain_gid = (unsigned long long)(a.chain_id_base + chain);
 
   const unsigned long long pair0 = (unsigned long long)a.step_offset >> 1;      // step_offset is even
@@ -79,8 +91,11 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
     sw0 = pairs_to < 0x7fffffff ? (int)pairs_to : 0x7fffffff;
   }
 
-  if (role == 1) {
+  if (role >= 1) {
     // ------------------------------------------------ producer ------------------------------------------------
+    // Producer pi fills chunks pi, pi + NP, pi + 2 NP, ... into its own two buffers pi and pi + NP (alternating), each with its
+    // own full / empty barrier pair shared with the consumer only.
+    const int pi = role - 1;
     const float scale = a.prop_scale ? a.prop_scale[chain] : 1.0f;
     float dscale[E];
 #pragma unroll
@@ -89,42 +104,45 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
     unsigned long long pair = pair0;
     gen.init(a.rk, c.sub, pair, chain_gid);
     long long left = n_pairs;
-    int sw = sw0, buf = 0;
-    long long chunk_no = 0;
+    int sw = sw0;
+    long long chunk_no = 0, mine = 0;
     while (left > 0) {
-      const int len = spec_chunk_len(left, sw);
-      if (chunk_no >= 2) named_bar_sync(2 + buf, 64);                            // buffer `buf` has been consumed
-      for (int p = 0; p < len; ++p) {
-        const unsigned long long pr = pair + (unsigned)p;
-        if ((uint32_t)(pr >> 32) != gen.hi32) gen.init(a.rk, c.sub, pr, chain_gid);
-        uint32_t w[4 * PairWords<E, PF>::NC];
-        gen.gen(a.rk, (uint32_t)pr, w);
-        float iA[E], iB[E], uA, uB;
-        uint32_t sA, sB;
-        pair_transform<E, IEEE, PF>(a, c, w, iA, iB, uA, uB, sA, sB, scale, dscale);
-        float v[4 * kSpecSlotF4];
+      const int len = spec_chunk_len<CH>(left, sw);
+      if ((int)(chunk_no % NP) == pi) {
+        const int buf = pi + NP * (int)(mine & 1);
+        if (mine >= 2) named_bar_sync(NB + buf, 64);                              // buffer `buf` has been consumed
+        for (int p = 0; p < len; ++p) {
+          const unsigned long long pr = pair + (unsigned)p;
+          if ((uint32_t)(pr >> 32) != gen.hi32) gen.init(a.rk, c.sub, pr, chain_gid);
+          uint32_t w[4 * PairWords<E, PF>::NC];
+          gen.gen(a.rk, (uint32_t)pr, w);
+          float iA[E], iB[E], uA, uB;
+          uint32_t sA, sB;
+          pair_transform<E, IEEE, PF>(a, c, w, iA, iB, uA, uB, sA, sB, scale, dscale);
+          float v[4 * SLOT];
 #pragma unroll
-        for (int q = 0; q < 4 * kSpecSlotF4; ++q) v[q] = 0.0f;
+          for (int q = 0; q < 4 * SLOT; ++q) v[q] = 0.0f;
 #pragma unroll
-        for (int e = 0; e < E; ++e) { v[e] = iA[e]; v[E + e] = iB[e]; }
-        v[2 * E] = uA; v[2 * E + 1] = uB;
-        v[2 * E + 2] = __uint_as_float(sA); v[2 * E + 3] = __uint_as_float(sB);
-        // CW == WT: slot = producer lane (the consumer lane of the same index reads it back); CW == 1: slot = sub * 8 + chain, so
-        // that the consumer lanes (one per chain) read consecutive float4
-        const int slot = CW == 1 ? c.sub * (32 / WT) + temp : lane;
+          for (int e = 0; e < E; ++e) { v[e] = iA[e]; v[E + e] = iB[e]; }
+          v[2 * E] = uA; v[2 * E + 1] = uB;
+          v[2 * E + 2] = __uint_as_float(sA); v[2 * E + 3] = __uint_as_float(sB);
+          // CW == WT: slot = producer lane (the consumer lane of the same index reads it back); CW == 1: slot = sub * CPW + chain,
+          // so that the consumer lanes (one per chain) read consecutive float4
+          const int slot = CW == 1 ? c.sub * CPW + cw : lane;
 #pragma unroll
-        for (int g = 0; g < kSpecSlotF4; ++g) ring[buf][p][g][slot] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          for (int g = 0; g < SLOT; ++g) ring[buf][p][g][slot] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+        named_bar_arrive(buf, 64);                                                // buffer `buf` is full
+        ++mine;
       }
-      named_bar_arrive(buf, 64);                                                  // buffer `buf` is full
       pair += (unsigned)len; left -= len;
       if (sweeps) sw -= len;
       if (sw == 0) sw = half_se;
-      buf ^= 1;
       ++chunk_no;
     }
     // match the consumer's last "empty" arrivals so that no barrier is left half-armed when the CTA retires
-    if (chunk_no >= 2) named_bar_sync(2 + buf, 64);
-    if (chunk_no >= 1) named_bar_sync(2 + (buf ^ 1), 64);
+    if (mine >= 2) named_bar_sync(NB + pi + NP * (int)(mine & 1), 64);
+    if (mine >= 1) named_bar_sync(NB + pi + NP * (int)((mine - 1) & 1), 64);
     return;
   }
 
@@ -133,7 +151,7 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
     constexpr int ET = E * WT;                                  // all coordinates of a chain in one thread
     const int kc = lane < K ? lane : K - 1;                     // lanes >= K shadow the hottest chain and never write
     const bool active = lane < K;
-    const long long ch = ladder * K + kc;
+    const long long ch = (long long)blockIdx.x * CPW + kc;
     Target<E, IEEE> tgt;                                        // the E-coordinate functor: evaluated WT times per density
     tgt.init(c);
     float x[ET];
@@ -178,11 +196,11 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
       lp = acc ? lpp : lp;
       cnt += acc ? 1u : 0u;
     };
-    unsigned long long pair = pair0;
-    long long left = n_pairs;
-    int sw = sw0, buf = 0;
+    long long left = n_pairs, chunk_no = 0;
+    int sw = sw0;
     while (left > 0) {
-      const int len = spec_chunk_len(left, sw);
+      const int len = spec_chunk_len<CH>(left, sw);
+      const int buf = (int)(chunk_no % NB);
       named_bar_sync(buf, 64);
       float jf = 0.0f;
       unsigned cnt = 0;
@@ -192,10 +210,10 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
         float iA[ET], iB[ET], uA = 0.0f, uB = 0.0f;
 #pragma unroll
         for (int v = 0; v < WT; ++v) {
-          float w[4 * kSpecSlotF4];
+          float w[4 * SLOT];
 #pragma unroll
-          for (int g = 0; g < kSpecSlotF4; ++g) {
-            const float4 t = ring[buf][p][g][v * (32 / WT) + kc];
+          for (int g = 0; g < SLOT; ++g) {
+            const float4 t = ring[buf][p][g][v * CPW + kc];
             w[4 * g] = t.x; w[4 * g + 1] = t.y; w[4 * g + 2] = t.z; w[4 * g + 3] = t.w;
           }
 #pragma unroll
@@ -206,8 +224,9 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
         step1(iA, uA, xo, jadd, jf, cnt);
         step1(iB, uB, xo, jadd, jf, cnt);
       }
-      named_bar_arrive(2 + buf, 64);
-      pair += (unsigned)len; left -= len;
+      named_bar_arrive(NB + buf, 64);
+      left -= len;
+      ++chunk_no;
       if (sweeps) sw -= len;
       if (sw == 0) {
         sw = half_se;
@@ -233,7 +252,6 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
         jf += ok ? j2 - jadd : 0.0f;
       }
       if (post) { jump_d += (double)jf; n_acc += cnt; }
-      buf ^= 1;
     }
     if (active) {
 #pragma unroll
@@ -291,20 +309,20 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
     cnt += acc ? 1u : 0u;
   };
 
-  unsigned long long pair = pair0;
-  long long left = n_pairs;
-  int sw = sw0, buf = 0;
+  long long left = n_pairs, chunk_no = 0;
+  int sw = sw0;
   while (left > 0) {
-    const int len = spec_chunk_len(left, sw);
+    const int len = spec_chunk_len<CH>(left, sw);
+    const int buf = (int)(chunk_no % NB);
     named_bar_sync(buf, 64);                                                      // wait until buffer `buf` is full
     float jf = 0.0f;
     unsigned cnt = 0;
     float xo[E], jadd = 0.0f;
     uint32_t spareB = 0u;
     for (int p = 0; p < len; ++p) {
-      float v[4 * kSpecSlotF4];
+      float v[4 * SLOT];
 #pragma unroll
-      for (int g = 0; g < kSpecSlotF4; ++g) {
+      for (int g = 0; g < SLOT; ++g) {
         const float4 t = ring[buf][p][g][lane];
         v[4 * g] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
       }
@@ -315,8 +333,9 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
       step(iA, v[2 * E], xo, jadd, jf, cnt);
       step(iB, v[2 * E + 1], xo, jadd, jf, cnt);
     }
-    named_bar_arrive(2 + buf, 64);                                                // buffer `buf` may be refilled
-    pair += (unsigned)len; left -= len;
+    named_bar_arrive(NB + buf, 64);                                               // buffer `buf` may be refilled
+    left -= len;
+    ++chunk_no;
     if (sweeps) sw -= len;
     if (sw == 0) {
       // adjacent-temperature sweep after the chunk's last step: reference semantics on the pre-sweep values, the pair's
@@ -346,7 +365,6 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
       jf += ok ? j2 - jadd : 0.0f;
     }
     if (post) { jump_d += (double)jf; n_acc += cnt; }
-    buf ^= 1;
   }
 
   jump_d = group_sum_f64_w<WT>(jump_d, WT);
@@ -361,14 +379,17 @@ __global__ void __launch_bounds__(64) mcmc_spec_kernel(const KernelArgs a) {
   }
 }
 
-template <template <int, bool> class Target, int E, int WT, int PF, int CW>
+// grid: one CTA per warp's worth of chains; the caller guarantees n_chains % (32 / WT) == 0 and E * WT == dim
+template <template <int, bool> class Target, int E, int WT, int PF, int CW, int NP>
 cudaError_t launch_mcmc_spec(const KernelArgs& a, cudaStream_t st) {
-  mcmc_spec_kernel<Target, E, WT, PF, CW><<<(unsigned)a.n_ladders, 64, 0, st>>>(a);
+  const long long grid = a.n_chains / (32 / WT);
+  mcmc_spec_kernel<Target, E, WT, PF, CW, NP><<<(unsigned)grid, 32 * (1 + NP), 0, st>>>(a);
   return cudaGetLastError();
 }
 
-// defined in rwmpt_inst_rough_carpet.cu: the tuned BASELINE config 3 shape (RoughCarpet without scaling block, 5 x 4, Normal);
-// consumer_lanes = 4 (fused kernel's mapping) or 1 (one consumer thread per chain)
-cudaError_t launch_mcmc_spec_rough_carpet_c3(const KernelArgs& a, int consumer_lanes, cudaStream_t st);
+// Per-family entry points, defined in the family's fast translation unit; cudaErrorNotSupported when the shape (elements per
+// lane, lanes per chain, consumer lanes, producers; Normal proposal) has no instantiation.
+cudaError_t launch_spec_rough_carpet(const KernelArgs& a, int E, int W, int consumer_lanes, int producers, cudaStream_t st);
+cudaError_t launch_spec_even_rosenbrock(const KernelArgs& a, int E, int W, int consumer_lanes, int producers, cudaStream_t st);
 
 }  // namespace rwmpt

@@ -786,9 +786,38 @@ def test_balanced_schedule_is_bit_identical_to_plain(store):
     torch.testing.assert_close(out[0][2], out[1][2], rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize("consumer_lanes", [4, 1])
+@pytest.mark.parametrize("d,producers", [(20, 1), (20, 2), (10, 1), (10, 2)])
+@pytest.mark.parametrize("burn,T1,T2", [(0, 3000, 0), (1001, 1501, 701)])
+def test_specialised_rwm_kernel_equals_fused_kernel(burn, T1, T2, d, producers, monkeypatch):
+    """BASELINE config 2's shapes (EvenRosenbrock d = 20 on 5 x 4, d = 10 on 5 x 2) on the warp-specialised kernel with one and
+    two producer warps per consumer warp, against the fused kernel: states, log-densities and acceptance counts bit for bit,
+    squared-jump sums to the grouping of their fp32 partial sums; odd burn-in, odd lengths, a resumed second call."""
+    dev = _cuda()
+    RWM, _ = _algs()
+    t = product_target(f"even_rosenbrock_d{d}")
+    x = {20: 0.297436, 10: 0.161282}[d]
+    monkeypatch.setenv("RWMPT_SPEC_NP", str(producers))
+    runs = {}
+    for sched in (1, 3):
+        np.random.seed(3)
+        algo = RWM(d, x * x / d, t, burn_in=burn, device=dev, num_chains=1024, seed=777, store="none")
+        algo._ensure_batch(1)
+        b = algo._batch
+        b.schedule = sched
+        b.run(T1)
+        if T2:
+            b.run(T2)
+        torch.cuda.synchronize()
+        runs[sched] = {k: getattr(b, k).cpu().numpy().copy() for k in ("state", "logp", "accept_count", "sq_jump_sum")}
+    for k in ("state", "logp", "accept_count"):
+        np.testing.assert_array_equal(runs[3][k], runs[1][k], err_msg=k)
+    np.testing.assert_allclose(runs[3]["sq_jump_sum"], runs[1]["sq_jump_sum"], rtol=2e-6, atol=1e-12)
+    assert runs[1]["accept_count"].sum() > 0
+
+
+@pytest.mark.parametrize("consumer_lanes,producers", [(4, 1), (1, 1), (4, 2)])
 @pytest.mark.parametrize("burn,T1,T2", [(0, 2000, 0), (101, 1501, 700), (2000, 777, 1224), (50, 65, 3)])
-def test_specialised_few_ladders_kernel_equals_fused_kernel(burn, T1, T2, consumer_lanes, monkeypatch):
+def test_specialised_few_ladders_kernel_equals_fused_kernel(burn, T1, T2, consumer_lanes, producers, monkeypatch):
     """The warp-specialised kernel of the few-ladders regime (producer warp: Philox + Box-Muller into a shared-memory ring,
     consumer warp: steps and sweeps; csrc/rwmpt_spec.cuh) against the fused kernel on BASELINE config 3's shape: states,
     log-densities, acceptance / swap counters and refresh indices bit for bit, squared-jump sums to the grouping of their fp32
@@ -798,6 +827,7 @@ def test_specialised_few_ladders_kernel_equals_fused_kernel(burn, T1, T2, consum
     _, PT = _algs()
     t = product_target("rough_carpet_d20")
     monkeypatch.setenv("RWMPT_SPEC_CW", str(consumer_lanes))   # consumer mapping: the fused kernel's 4 lanes per chain, or 1 thread
+    monkeypatch.setenv("RWMPT_SPEC_NP", str(producers))        # producer warps per consumer warp
     runs = {}
     for sched in (1, 3):                                      # RWMPT_SCHEDULE_PLAIN, RWMPT_SCHEDULE_SPECIALISED
         algo = PT(20, 0.9, t, geom_temp_spacing=True, swap_every=10, burn_in=burn, device=dev, num_ladders=96, store="none",
