@@ -15,10 +15,12 @@ namespace rwmpt {
 
 static thread_local char g_err[512] = "";
 
-// warp-specialised kernel for RWM (config 2): producers per consumer warp, and the auto rule's bound on the fused kernel's
-// warps per SM (set from measurements, profiles/r2_specialised_kernel.txt)
-constexpr int kSpecRwmProducers = 2;
-constexpr int kSpecRwmAutoWarpsPerSm = 0;   // 0: never automatically (RWMPT_SCHEDULE_SPECIALISED only) until measured
+// warp-specialised kernel for RWM (config 2), from measurements (profiles/r2_specialised_kernel.txt): 4096 chains of d = 10
+// (256 fused warps) +57 % with three producer warps per consumer warp, d = 20 (512 fused warps) +7 % with two; more
+// producers lose again (the machine's integer-multiply / issue capacity, not the consumer, is the limit).  Auto rule: up
+// to 4 fused-kernel warps per SM.
+constexpr int kSpecRwmAutoWarpsPerSm = 4;
+static int spec_rwm_producers(int lanes_per_chain) { return lanes_per_chain == 2 ? 3 : 2; }
 
 // family name (RWMPT_FAMILY_LIST) -> enum of include/rwmpt.h
 #define RWMPT_FAMILY_ID_rough_carpet RWMPT_T_ROUGH_CARPET
@@ -341,7 +343,7 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
     const char* ecw = getenv("RWMPT_SPEC_CW");
     const char* enp = getenv("RWMPT_SPEC_NP");
     const int spec_cw = ecw ? atoi(ecw) : g.W;
-    const int spec_np = enp ? atoi(enp) : (spec_rwm ? kSpecRwmProducers : 1);
+    const int spec_np = enp ? atoi(enp) : (spec_rwm ? spec_rwm_producers(g.W) : 1);
     const int64_t O = r->step_offset, N = r->n_steps, B = r->burn_in;
     int64_t head = O >= B ? 0 : B - O;          // steps that end at burn-in ...
     if ((O + head) & 1) ++head;                 // ... or one later, so that the middle starts on an even step

@@ -11,10 +11,16 @@ namespace rwmpt {
 cudaError_t launch_spec_even_rosenbrock(const KernelArgs& a, int E, int W, int consumer_lanes, int producers, cudaStream_t st) {
   if (a.prop_family != RWMPT_P_NORMAL || E != 5 || a.dim != E * W) return cudaErrorNotSupported;
   (void)consumer_lanes;
-  if (W == 4) return producers == 2 ? launch_mcmc_spec<EvenRosenbrock, 5, 4, RWMPT_P_NORMAL, 4, 2>(a, st)
-                                    : launch_mcmc_spec<EvenRosenbrock, 5, 4, RWMPT_P_NORMAL, 4, 1>(a, st);
-  if (W == 2) return producers == 2 ? launch_mcmc_spec<EvenRosenbrock, 5, 2, RWMPT_P_NORMAL, 2, 2>(a, st)
-                                    : launch_mcmc_spec<EvenRosenbrock, 5, 2, RWMPT_P_NORMAL, 2, 1>(a, st);
+  switch (W * 10 + producers) {
+    case 41: return launch_mcmc_spec<EvenRosenbrock, 5, 4, RWMPT_P_NORMAL, 4, 1>(a, st);
+    case 42: return launch_mcmc_spec<EvenRosenbrock, 5, 4, RWMPT_P_NORMAL, 4, 2>(a, st);
+    case 43: return launch_mcmc_spec<EvenRosenbrock, 5, 4, RWMPT_P_NORMAL, 4, 3>(a, st);
+    case 44: return launch_mcmc_spec<EvenRosenbrock, 5, 4, RWMPT_P_NORMAL, 4, 4>(a, st);
+    case 21: return launch_mcmc_spec<EvenRosenbrock, 5, 2, RWMPT_P_NORMAL, 2, 1>(a, st);
+    case 22: return launch_mcmc_spec<EvenRosenbrock, 5, 2, RWMPT_P_NORMAL, 2, 2>(a, st);
+    case 23: return launch_mcmc_spec<EvenRosenbrock, 5, 2, RWMPT_P_NORMAL, 2, 3>(a, st);
+    case 24: return launch_mcmc_spec<EvenRosenbrock, 5, 2, RWMPT_P_NORMAL, 2, 4>(a, st);
+  }
   return cudaErrorNotSupported;
 }
 }  // namespace rwmpt

@@ -29,12 +29,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // geometry of the ring: SLOT float4 per lane and pair (2E increments, 2 log-uniforms, 2 spare words), NB = 2 NP buffers of CH
-// pairs each, about 32 KiB in all
+// pairs each, at most 48 KiB in all
 template <int E, int NP>
 struct SpecRing {
   static constexpr int SLOT = (2 * E + 4 + 3) / 4;
   static constexpr int NB = 2 * NP;
-  static constexpr int CH_RAW = (32 * 1024) / (NB * SLOT * 512);
+  static constexpr int CH_RAW = (48 * 1024) / (NB * SLOT * 512);   // static shared memory: 48 KiB
   static constexpr int CH = CH_RAW < 1 ? 1 : (CH_RAW > 8 ? 8 : CH_RAW);
 };
 
