@@ -330,7 +330,7 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   const int cpw = 32 / g.W;
   const bool spec_common = !ieee && !test_mode && !r->samples && r->proposal_family == RWMPT_P_NORMAL && g.E * g.W == d &&
                            n_chains_all % cpw == 0 && n_chains_all / cpw <= 2147483647LL;
-  const bool spec_pt = spec_common && r->target.family == RWMPT_T_ROUGH_CARPET && a.target_plain && r->n_temps == 8 && g.W == 4 &&
+  const bool spec_pt = spec_common && r->target.family == RWMPT_T_ROUGH_CARPET && a.target_plain && r->n_temps == 8 && g.W == 4 && g.E == 5 &&
                        (a.swap_every & 1) == 0 && r->swap_mode == RWMPT_SWAP_REFERENCE;
   const bool spec_rwm = spec_common && r->target.family == RWMPT_T_EVEN_ROSENBROCK && r->n_temps == 1 && g.E == 5 && (g.W == 4 || g.W == 2);
   const long long fused_warps = n_chains_all / cpw;
@@ -357,13 +357,12 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
         s.step_offset = segs[k][0];
         s.n_steps = segs[k][1];
         s.rounds_before = count_rounds(0, s.step_offset, r->burn_in, a.swap_every);
-        cudaError_t e;
-        if (k == 1) {
+        cudaError_t e = cudaErrorNotSupported;
+        if (k == 1)
           e = spec_pt ? launch_spec_rough_carpet(s, g.E, g.W, spec_cw, spec_np, (cudaStream_t)stream)
                       : launch_spec_even_rosenbrock(s, g.E, g.W, spec_cw, spec_np, (cudaStream_t)stream);
-        } else {
-          e = dispatch_mcmc(r->target.family, s, g, ieee, (cudaStream_t)stream);
-        }
+        // no instantiation for this shape / producer count (e.g. an RWMPT_SPEC_NP outside 1..4): the fused kernel runs the middle too
+        if (e == cudaErrorNotSupported) e = dispatch_mcmc(r->target.family, s, g, ieee, (cudaStream_t)stream);
         if (e != cudaSuccess) return cuda_fail(e, k == 1 ? "specialised mcmc kernel launch" : "mcmc kernel launch");
       }
       return RWMPT_OK;

@@ -845,6 +845,30 @@ def test_specialised_few_ladders_kernel_equals_fused_kernel(burn, T1, T2, consum
     assert runs[1]["accept_count"].sum() > 0 and (burn + 10 >= T1 + T2 or runs[1]["swap_accepts"].sum() > 0)
 
 
+def test_few_ladder_shapes_without_a_specialised_instantiation_run_on_the_fused_kernel(monkeypatch):
+    """The auto schedule only takes the specialised kernel for shapes it is instantiated for; a neighbouring shape (RoughCarpet
+    d = 16 on 4 x 4, 8 temperatures, few ladders) and an out-of-range producer count must run on the fused kernel, with the same
+    results as the plain schedule."""
+    dev = _cuda()
+    _, PT = _algs()
+    import rwm_pt_pytorch_b200.target_distributions as td
+    out = {}
+    for tag, d, env in (("d16", 16, {}), ("d20_np9", 20, {"RWMPT_SPEC_NP": "9"})):
+        t = td.RoughCarpetDistributionTorch(d, device=torch.device("cpu"))
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for sched in (1, 0, 3):
+            algo = PT(d, 0.9, t, geom_temp_spacing=True, swap_every=10, burn_in=100, device=dev, num_ladders=64, store="none", seed=5,
+                      swap_mode="reference")
+            algo._batch.schedule = sched
+            algo.generate_samples(1900)
+            out[(tag, sched)] = (algo._batch.state.cpu().numpy().copy(), algo._batch.accept_count.cpu().numpy().copy(), algo.num_swap_acceptances)
+        for sched in (0, 3):
+            np.testing.assert_array_equal(out[(tag, sched)][0], out[(tag, 1)][0])
+            np.testing.assert_array_equal(out[(tag, sched)][1], out[(tag, 1)][1])
+            assert out[(tag, sched)][2] == out[(tag, 1)][2] > 0
+
+
 def test_full_size_config3_properties():
     """BASELINE config 3 at its full width (1024 ladders x 8 temperatures, RoughCarpet d=20, swap_every 10, burn-in 2000):
     size-independent properties instead of an oracle run -- (a) one launch == two resumed launches, (b) two shards of 512
