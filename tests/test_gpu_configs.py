@@ -107,3 +107,35 @@ def test_config5_variance_sweep_matches_oracle(key):
               f"ESJD {esjd[i].mean():.6f} vs {e_o.mean():.6f}")
         assert abs(acc[i].mean() - a_o.mean()) <= 3 * a_err, (key, i, acc[i].mean(), a_o.mean(), a_err)
         assert abs(esjd[i].mean() - e_o.mean()) <= 3 * e_err + 0.02 * e_o.mean(), (key, i, esjd[i].mean(), e_o.mean(), e_err)
+
+
+# ---- how far the fast-math accept rule is from the IEEE one ---------------------------------------------------------
+@pytest.mark.parametrize("key,d,x", [("rough_carpet_d20", 20, 0.9 ** 0.5 * 20 ** 0.5), ("even_rosenbrock_d20", 20, 0.297436),
+                                     ("three_mixture_pm15_d50", 50, 2.38), ("full_rosenbrock_d100", 100, 0.34),
+                                     ("neal_funnel_d100", 100, 1.0)])
+def test_fast_math_accept_probability_is_close_to_ieee(key, d, x):
+    """Fast mode (MUFU ex2 / lg2, FMA contraction, packed fp32, fewer logarithms) only matters through the accept rule
+    u < exp(beta (lp' - lp)): a decision can differ from the IEEE kernel's only when u falls between the two probabilities.
+    On states of a real chain and real proposals, the probability of such a flip, E|p_fast - p_ieee|, is bounded here per
+    BASELINE target (measured: 1e-7 ... 3e-6; the statistical tests then bound the accumulated effect)."""
+    dev = _cuda()
+    t = product_target(key)
+    var = x * x / d
+    np.random.seed(1)
+    algo = _rwm()(d, var, t, burn_in=0, device=dev, num_chains=4096, seed=11, store="none")
+    algo.generate_samples(2000)                                 # states from the chain itself, not from a synthetic cloud
+    cur = algo._batch.state.clone()
+    g = torch.Generator(device=dev).manual_seed(5)
+    prop = cur + torch.randn(cur.shape, device=dev, generator=g) * var ** 0.5
+    lp = {}
+    for mode in ("fast", "ieee"):
+        t.math_mode = mode
+        lp[mode] = (t.log_density(cur).double(), t.log_density(prop).double())
+    t.math_mode = "fast"
+    p = {m: torch.exp(torch.clamp(lp[m][1] - lp[m][0], max=0.0)) for m in lp}
+    gap = (p["fast"] - p["ieee"]).abs()
+    rel_lp = ((lp["fast"][0] - lp["ieee"][0]).abs() / lp["ieee"][0].abs().clamp(min=1.0)).max().item()
+    print(f"[fast vs ieee {key}] E|dp| = {gap.mean().item():.3e}, max |dp| = {gap.max().item():.3e}, max rel |d lp| = {rel_lp:.3e}, "
+          f"mean accept probability {p['ieee'].mean().item():.3f}")
+    assert 0.02 < p["ieee"].mean().item() < 0.98               # proposals in the regime the sampler works in
+    assert gap.mean().item() < 2e-5 and gap.max().item() < 2e-3, (gap.mean().item(), gap.max().item())

@@ -602,6 +602,18 @@ def test_proposal_plugin_samplers_moments():
         s = UniformRadiusProposal(d2, 2.0, 1.0, dev, torch.float32).sample(m)
         rr = s.norm(dim=1)
         assert rr.max().item() <= 2.0 * (1 + 1e-5) and abs((rr ** 2).mean().item() - 4.0 * d2 / (d2 + 2)) < 0.03 * 4.0
+    # the flat form (d % 4 == 0, aligned output: one Philox call -> one float4 per thread) and the grouped form (here forced
+    # by an output pointer that is only 4-byte aligned) use the same counters: identical values
+    import ctypes as C
+    from rwm_pt_pytorch_b200 import _lib
+    lib = _lib.load()
+    for fam in (0, 1):
+        a = torch.empty(1000 * 20 + 4, device=dev)
+        b = torch.empty(1000 * 20 + 4, device=dev)
+        ds = torch.linspace(0.5, 1.5, 20, device=dev) if fam == 1 else None
+        _lib.check(lib.rwmpt_proposal_sample(fam, 20, 0.7, _lib.ptr(ds), 1000, 99, 5, a.data_ptr(), _lib.stream_ptr(dev)))
+        _lib.check(lib.rwmpt_proposal_sample(fam, 20, 0.7, _lib.ptr(ds), 1000, 99, 5, b.data_ptr() + 4, _lib.stream_ptr(dev)))
+        assert torch.equal(a[:20000], b[1:20001])
 
 
 @pytest.mark.parametrize("swap_mode", ["reference", "exchange"])
