@@ -103,12 +103,14 @@ def job_gpu_indices(world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons of the JOB's GPUs, sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons of the JOB's GPUs, sampled every 200 ms while the timed region runs.  The poller is
+    started during the last warm-up step (its start-up -- NVML initialisation -- stalled the first timed launch by ~25 ms when
+    it was started at the timed region's edge); `mark()` at the start of the timed region drops the rows read before it."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, indices):
-        self.indices, self.rows, self.proc = list(indices), [], None
+        self.indices, self.rows, self.proc, self.t0 = list(indices), [], None, 0.0
 
     def start(self):
         try:
@@ -121,7 +123,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -132,7 +137,7 @@ class ClockSampler:
             self.proc.wait(timeout=10)   # NVML polling stalls cudaMalloc / cudaFree of later phases: make sure it is gone
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        rows = [r for r in self.rows if len(r) >= 9 and r[0].isdigit() and int(r[0]) in self.indices]
+        rows = [r for t, r in self.rows if t >= self.t0 and len(r) >= 9 and r[0].isdigit() and int(r[0]) in self.indices]
         sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -654,7 +659,12 @@ def main():
             batch.allocate_storage(store, T + 2, 1, with_logp=True)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
         reduced = None
-        for _ in range(warmup):
+        # one nvidia-smi poller per job (rank 0), restricted to the job's own GPUs: NVML queries take a driver lock that CUDA
+        # calls of the same process tree can wait on, and idle GPUs of the box would drag the median down
+        sampler = ClockSampler(job_gpu_indices(world) if world > 1 else [job_gpu_indices(local + 1)[local]]) if (with_clocks and rank == 0) else None
+        for w in range(warmup):
+            if sampler and w == warmup - 1:
+                sampler.start()                                           # start-up cost lands in the last warm-up step
             batch.rewind_storage()
             batch.run(T)
             if world > 1:                                                 # also warms the NCCL communicator up
@@ -663,11 +673,10 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        # one nvidia-smi poller per job (rank 0), restricted to the job's own GPUs: NVML queries take a driver lock that CUDA
-        # calls of the same process tree can wait on, and idle GPUs of the box would drag the median down
-        sampler = ClockSampler(job_gpu_indices(world) if world > 1 else [job_gpu_indices(local + 1)[local]]) if (with_clocks and rank == 0) else None
         if sampler:
-            sampler.start()
+            if sampler.proc is None:
+                sampler.start()                                           # --warmup 0
+            sampler.mark()                                                # rows from here on belong to the timed region
         evs = []
         launches = 0
         for _ in range(steps):

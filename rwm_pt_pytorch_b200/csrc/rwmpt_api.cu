@@ -16,11 +16,12 @@ namespace rwmpt {
 static thread_local char g_err[512] = "";
 
 // warp-specialised kernel for RWM (config 2), from measurements (profiles/r2_specialised_kernel.txt): 4096 chains of d = 10
-// (256 fused warps) +57 % with three producer warps per consumer warp, d = 20 (512 fused warps) +7 % with two; more
+// (256 fused warps) +57 % with three producer warps per consumer warp, d = 20 (512 fused warps) +7 % with two, d = 30 on 8 x 4
+// (512 fused warps, two padding coordinates) +37 % with two (1.41e10 -> 1.93e10; three: the same, four: -2 %); more
 // producers lose again (the machine's integer-multiply / issue capacity, not the consumer, is the limit).  Auto rule: up
 // to 4 fused-kernel warps per SM.
 constexpr int kSpecRwmAutoWarpsPerSm = 4;
-static int spec_rwm_producers(int lanes_per_chain) { return lanes_per_chain == 2 ? 3 : 2; }
+static int spec_rwm_producers(int elems_per_lane, int lanes_per_chain) { return elems_per_lane == 8 ? 2 : (lanes_per_chain == 2 ? 3 : 2); }
 
 // family name (RWMPT_FAMILY_LIST) -> enum of include/rwmpt.h
 #define RWMPT_FAMILY_ID_rough_carpet RWMPT_T_ROUGH_CARPET
@@ -127,6 +128,13 @@ static int pick_geometry(int d, int K, long long n_ladders, bool ieee, int want_
       d > 49 && d <= 56 && K * 8 <= kMaxCtaThreads) {
     bestE = 7;
     bestW = 8;
+  }
+  // BASELINE config 2 at d = 30 (any 24 < d <= 32): EvenRosenbrock RWM with a Normal proposal runs the tuned 8 x 4 kernel -- the
+  // score above would take 4 x 8 for 4096 chains; measured 1.41e10 against 1.14e10 chain-steps/s fused, and 8 x 4 is the shape the
+  // warp-specialised kernel is instantiated for (1.93e10, profiles/r2_specialised_kernel.txt)
+  if (!ieee && for_mcmc && want_W <= 0 && family == RWMPT_T_EVEN_ROSENBROCK && pf == RWMPT_P_NORMAL && K == 1 && d > 24 && d <= 32) {
+    bestE = 8;
+    bestW = 4;
   }
   g->variant = 0;
   if (!ieee && for_mcmc) {
@@ -322,17 +330,20 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
   // Few warps per GPU (strong scaling of config 3, config 2's 4096 chains): the warp-specialised kernel (rwmpt_spec.cuh) takes the
   // regular middle of the run, mcmc_kernel the edges -- up to the first even step at or past burn-in, and an odd last step --
   // each launch resuming the previous one exactly (state, log-density, accumulators and Philox offsets are all functions of
-  // step_offset).  Shapes: chains fill whole warps without padding (E * W == dim), Normal proposal, accumulators only; for a
+  // step_offset).  Shapes: chains fill whole warps (E * W == dim, or EvenRosenbrock 24 < d <= 32 on 8 x 4), Normal proposal, accumulators only; for a
   // ladder: 8 temperatures x 4 lanes = one warp, swap_every even, the reference's swap semantics.
   // Auto: PT up to 3.5 ladders per SM (measured: +40 % at 64-296 ladders per GPU, +8 % at 512, -24 % at 1024); RWM see below.
   // RWMPT_SCHEDULE_SPECIALISED forces it where eligible; RWMPT_SPEC_CW / RWMPT_SPEC_NP choose the consumer mapping / producers.
   const long long n_chains_all = r->n_ladders * r->n_temps;
   const int cpw = 32 / g.W;
-  const bool spec_common = !ieee && !test_mode && !r->samples && r->proposal_family == RWMPT_P_NORMAL && g.E * g.W == d &&
+  const bool spec_common = !ieee && !test_mode && !r->samples && r->proposal_family == RWMPT_P_NORMAL &&
                            n_chains_all % cpw == 0 && n_chains_all / cpw <= 2147483647LL;
-  const bool spec_pt = spec_common && r->target.family == RWMPT_T_ROUGH_CARPET && a.target_plain && r->n_temps == 8 && g.W == 4 && g.E == 5 &&
+  const bool spec_exact = g.E * g.W == d;
+  const bool spec_pt = spec_common && spec_exact && r->target.family == RWMPT_T_ROUGH_CARPET && a.target_plain && r->n_temps == 8 && g.W == 4 && g.E == 5 &&
                        (a.swap_every & 1) == 0 && r->swap_mode == RWMPT_SWAP_REFERENCE;
-  const bool spec_rwm = spec_common && r->target.family == RWMPT_T_EVEN_ROSENBROCK && r->n_temps == 1 && g.E == 5 && (g.W == 4 || g.W == 2);
+  const bool spec_rwm = spec_common && r->target.family == RWMPT_T_EVEN_ROSENBROCK && r->n_temps == 1 &&
+                        ((spec_exact && g.E == 5 && (g.W == 4 || g.W == 2)) || (g.E == 8 && g.W == 4 && d > 24 && d <= 32) ||
+                         (g.E == 4 && g.W == 8 && d > 28 && d <= 32));   // d = 30: two padding coordinates
   const long long fused_warps = n_chains_all / cpw;
   bool spec_want = r->schedule == RWMPT_SCHEDULE_SPECIALISED;
   if (r->schedule == RWMPT_SCHEDULE_AUTO && g.sms > 0) {
@@ -343,7 +354,7 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
     const char* ecw = getenv("RWMPT_SPEC_CW");
     const char* enp = getenv("RWMPT_SPEC_NP");
     const int spec_cw = ecw ? atoi(ecw) : g.W;
-    const int spec_np = enp ? atoi(enp) : (spec_rwm ? spec_rwm_producers(g.W) : 1);
+    const int spec_np = enp ? atoi(enp) : (spec_rwm ? spec_rwm_producers(g.E, g.W) : 1);
     const int64_t O = r->step_offset, N = r->n_steps, B = r->burn_in;
     int64_t head = O >= B ? 0 : B - O;          // steps that end at burn-in ...
     if ((O + head) & 1) ++head;                 // ... or one later, so that the middle starts on an even step

@@ -17,7 +17,8 @@
 // counters are bit-identical and the squared-jump sums agree to the grouping of their fp32 partial sums
 // (tests/test_gpu_parity.py::test_specialised_*).  The kernel takes only the regular part of a run -- an even number of steps
 // from an even offset, all on one side of the burn-in boundary, swap_every even, chains that fill whole warps without padding
-// (for PT: a ladder that fills exactly one warp), accumulators only; the host (rwmpt_api.cu) runs the edges through
+// (for PT: a ladder that fills exactly one warp; config 2's d = 30 runs on 8 x 4 lanes with two masked padding coordinates),
+// accumulators only; the host (rwmpt_api.cu) runs the edges through
 // mcmc_kernel, which is resumable by construction.
 #pragma once
 
@@ -49,14 +50,16 @@ __device__ __forceinline__ int spec_chunk_len(long long left, int sw) {
 // CW = consumer lanes per chain: WT (the consumer keeps the fused kernel's lane mapping) or 1 (ONE consumer thread per chain: it
 // holds all E*WT coordinates, evaluates the WT lane partials of the density itself -- independent instruction streams instead
 // of a shuffle butterfly -- and adds them in the butterfly's order, so the log-density is bit-identical; measured 2x slower
-// (issue-bound), kept as a knob for the RoughCarpet 5 x 4 shape).  NP = producer warps.
-template <template <int, bool> class Target, int E, int WT, int PF, int CW, int NP>
+// (issue-bound), kept as a knob for the RoughCarpet 5 x 4 shape).  NP = producer warps.  EXACT = false: E * WT > dim, the last
+// lanes of a chain carry padding coordinates (config 2's d = 30 on 8 x 4) -- masked exactly as in mcmc_unit.
+template <template <int, bool> class Target, int E, int WT, int PF, int CW, int NP, bool EXACT = true>
 __global__ void __launch_bounds__(32 * (1 + NP)) mcmc_spec_kernel(const KernelArgs a) {
   using R = SpecRing<E, NP>;
   constexpr int SLOT = R::SLOT, NB = R::NB, CH = R::CH;
   constexpr int CPW = 32 / WT;                                // chains per warp
   static_assert(CW == WT || CW == 1, "consumer lanes per chain: WT or 1");
   static_assert(CW == WT || WT == 4, "the one-thread-per-chain consumer is written for four producer lanes per chain");
+  static_assert(CW == WT || EXACT, "the one-thread-per-chain consumer has no padding masks");
   constexpr bool IEEE = false;
   using M = Mth<IEEE>;
   __shared__ float4 ring[NB][CH][SLOT][32];                   // [buffer][pair][word group][slot]: conflict-free LDS.128 / STS.128
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(32 * (1 + NP)) mcmc_spec_kernel(const KernelAr
   const int K = a.K, d = a.dim;
   const int lane = (int)threadIdx.x & 31;
   const int role = (int)threadIdx.x >> 5;                   // 0: consumer (steps), 1 .. NP: producers (randomness)
-  CtxT<WT, true> c;
+  CtxT<WT, EXACT> c;
   c.P = a.P; c.d = d; c.W = WT;
   c.sub = lane % WT;
   c.base = c.sub * E;
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(32 * (1 + NP)) mcmc_spec_kernel(const KernelAr
     const float scale = a.prop_scale ? a.prop_scale[chain] : 1.0f;
     float dscale[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) dscale[e] = a.prop_dim_scale ? a.prop_dim_scale[c.base + e] : 1.0f;
+    for (int e = 0; e < E; ++e) dscale[e] = c.ok(e) ? (a.prop_dim_scale ? a.prop_dim_scale[c.base + e] : 1.0f) : 0.0f;
     PhiloxPairGen<PairWords<E, PF>::NC> gen;
     unsigned long long pair = pair0;
     gen.init(a.rk, c.sub, pair, chain_gid);
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(32 * (1 + NP)) mcmc_spec_kernel(const KernelAr
   tgt.init(c);
   float x[E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) x[e] = a.state[chain * d + c.base + e];
+  for (int e = 0; e < E; ++e) x[e] = c.ok(e) ? a.state[chain * d + c.base + e] : 0.0f;
   float lp = a.logp[chain];
   const float beta = a.beta[chain];
   const float beta_next = __shfl_down_sync(kFull, beta, WT);
@@ -277,23 +280,32 @@ __global__ void __launch_bounds__(32 * (1 + NP)) mcmc_spec_kernel(const KernelAr
   double jump_d = 0.0;
   long long round_local = 0;
 
-  // one Metropolis step on the lane's coordinates: the arithmetic of mcmc_unit's plain_step (packed fp32, EXACT mapping)
+  // one Metropolis step on the lane's coordinates: the arithmetic of mcmc_unit's plain_step (packed fp32 on an EXACT mapping,
+  // scalar with the padding masks otherwise)
   auto step = [&](const float (&inc)[E], const float u, float (&xo)[E], float& jadd, float& jf, unsigned& cnt) {
     float prop[E];
-    float j2;
-    f32x2_t j2p = pack2(0.0f, 0.0f);
+    float j2 = 0.0f;
+    if constexpr (EXACT && kUseF32x2 && E >= 2) {
+      f32x2_t j2p = pack2(0.0f, 0.0f);
 #pragma unroll
-    for (int e = 0; e + 1 < E; e += 2) {
-      const f32x2_t i2 = pack2(inc[e], inc[e + 1]);
-      unpack2(add2(pack2(x[e], x[e + 1]), i2), prop[e], prop[e + 1]);
-      j2p = fma2(i2, i2, j2p);
-    }
-    float ja, jb;
-    unpack2(j2p, ja, jb);
-    j2 = ja + jb;
-    if constexpr (E & 1) {
-      prop[E - 1] = x[E - 1] + inc[E - 1];
-      j2 = fmaf(inc[E - 1], inc[E - 1], j2);
+      for (int e = 0; e + 1 < E; e += 2) {
+        const f32x2_t i2 = pack2(inc[e], inc[e + 1]);
+        unpack2(add2(pack2(x[e], x[e + 1]), i2), prop[e], prop[e + 1]);
+        j2p = fma2(i2, i2, j2p);
+      }
+      float ja, jb;
+      unpack2(j2p, ja, jb);
+      j2 = ja + jb;
+      if constexpr (E & 1) {
+        prop[E - 1] = x[E - 1] + inc[E - 1];
+        j2 = fmaf(inc[E - 1], inc[E - 1], j2);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        prop[e] = c.ok(e) ? M::add(x[e], inc[e]) : 0.0f;
+        j2 = c.ok(e) ? fmaf(inc[e], inc[e], j2) : j2;
+      }
     }
     const float lpp = tgt.logp(prop, c);
     const float lar = M::mul(beta, M::sub(lpp, lp));
@@ -369,7 +381,8 @@ __global__ void __launch_bounds__(32 * (1 + NP)) mcmc_spec_kernel(const KernelAr
 
   jump_d = group_sum_f64_w<WT>(jump_d, WT);
 #pragma unroll
-  for (int e = 0; e < E; ++e) a.state[chain * d + c.base + e] = x[e];
+  for (int e = 0; e < E; ++e)
+    if (c.ok(e)) a.state[chain * d + c.base + e] = x[e];
   if (lead) {
     a.logp[chain] = lp;
     if (a.accept_count) a.accept_count[chain] += n_acc;
@@ -379,11 +392,12 @@ __global__ void __launch_bounds__(32 * (1 + NP)) mcmc_spec_kernel(const KernelAr
   }
 }
 
-// grid: one CTA per warp's worth of chains; the caller guarantees n_chains % (32 / WT) == 0 and E * WT == dim
-template <template <int, bool> class Target, int E, int WT, int PF, int CW, int NP>
+// grid: one CTA per warp's worth of chains; the caller guarantees n_chains % (32 / WT) == 0 and E * WT == dim (EXACT) or
+// E * WT >= dim (otherwise)
+template <template <int, bool> class Target, int E, int WT, int PF, int CW, int NP, bool EXACT = true>
 cudaError_t launch_mcmc_spec(const KernelArgs& a, cudaStream_t st) {
   const long long grid = a.n_chains / (32 / WT);
-  mcmc_spec_kernel<Target, E, WT, PF, CW, NP><<<(unsigned)grid, 32 * (1 + NP), 0, st>>>(a);
+  mcmc_spec_kernel<Target, E, WT, PF, CW, NP, EXACT><<<(unsigned)grid, 32 * (1 + NP), 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -798,16 +798,18 @@ def test_balanced_schedule_is_bit_identical_to_plain(store):
     torch.testing.assert_close(out[0][2], out[1][2], rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize("d,producers", [(20, 1), (20, 2), (10, 1), (10, 2)])
+@pytest.mark.parametrize("d,producers", [(20, 1), (20, 2), (10, 1), (10, 2), (30, 1), (30, 2), (30, 3), (26, 2), (32, 2)])
 @pytest.mark.parametrize("burn,T1,T2", [(0, 3000, 0), (1001, 1501, 701)])
 def test_specialised_rwm_kernel_equals_fused_kernel(burn, T1, T2, d, producers, monkeypatch):
-    """BASELINE config 2's shapes (EvenRosenbrock d = 20 on 5 x 4, d = 10 on 5 x 2) on the warp-specialised kernel with one and
-    two producer warps per consumer warp, against the fused kernel: states, log-densities and acceptance counts bit for bit,
+    """BASELINE config 2's shapes (EvenRosenbrock d = 20 on 5 x 4, d = 10 on 5 x 2, d = 30 -- and its neighbours 26 and 32 -- on
+    8 x 4 with masked padding coordinates) on the warp-specialised kernel with one to three producer warps per consumer warp,
+    against the fused kernel: states, log-densities and acceptance counts bit for bit,
     squared-jump sums to the grouping of their fp32 partial sums; odd burn-in, odd lengths, a resumed second call."""
     dev = _cuda()
     RWM, _ = _algs()
-    t = product_target(f"even_rosenbrock_d{d}")
-    x = {20: 0.297436, 10: 0.161282}[d]
+    import rwm_pt_pytorch_b200.target_distributions as td
+    t = td.EvenRosenbrockTorch(d, device=torch.device("cpu"))
+    x = {20: 0.297436, 10: 0.161282}.get(d, 0.3)
     monkeypatch.setenv("RWMPT_SPEC_NP", str(producers))
     runs = {}
     for sched in (1, 3):
@@ -815,6 +817,7 @@ def test_specialised_rwm_kernel_equals_fused_kernel(burn, T1, T2, d, producers, 
         algo = RWM(d, x * x / d, t, burn_in=burn, device=dev, num_chains=1024, seed=777, store="none")
         algo._ensure_batch(1)
         b = algo._batch
+        assert b.geometry() == {10: (5, 2), 20: (5, 4)}.get(d, (8, 4))   # the shapes the specialised kernel is instantiated for
         b.schedule = sched
         b.run(T1)
         if T2:
