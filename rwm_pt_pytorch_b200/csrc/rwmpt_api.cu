@@ -408,22 +408,36 @@ __global__ void __launch_bounds__(128) proposal_kernel(int family, int d, int G,
     if (family == RWMPT_P_UNIFORM_RADIUS) {
       // pass 1: squared norm of the row's normal vector (uniform.py:48-73: z / ||z|| * R * u^(1/d))
       float n2 = 0.0f;
-      for (int b = sub; b < n_blk; b += G) {
-        const uint4 w = philox4x32_10((unsigned)b, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
-        float z[4];
-        box_muller<false>(w.x, w.y, z[0], z[1]);
-        box_muller<false>(w.z, w.w, z[2], z[3]);
+      unsigned uw;
+      if (one_block && n_blk < G) {
+        // the group has idle lanes (d = 20: 5 blocks on 8 lanes): the first of them draws the row's radius word in the same Philox
+        // call the others draw their normals in -- one call per lane instead of two, same counters, same values
+        const uint4 w = philox4x32_10(sub < n_blk ? (unsigned)sub : 0xffffffffu, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
+        box_muller<false>(w.x, w.y, zk[0], zk[1]);
+        box_muller<false>(w.z, w.w, zk[2], zk[3]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (4 * b + q < d) n2 = fmaf(z[q], z[q], n2);
-          zk[q] = z[q];
+        for (int q = 0; q < 4; ++q)
+          if (sub < n_blk && 4 * sub + q < d) n2 = fmaf(zk[q], zk[q], n2);
+        for (int o = G >> 1; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFull, n2, o);
+        uw = __shfl_sync(kFull, w.x, (lane & ~(G - 1)) + n_blk);
+      } else {
+        for (int b = sub; b < n_blk; b += G) {
+          const uint4 w = philox4x32_10((unsigned)b, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
+          float z[4];
+          box_muller<false>(w.x, w.y, z[0], z[1]);
+          box_muller<false>(w.z, w.w, z[2], z[3]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (4 * b + q < d) n2 = fmaf(z[q], z[q], n2);
+            zk[q] = z[q];
+          }
         }
+        for (int o = G >> 1; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFull, n2, o);
+        uw = philox4x32_10(0xffffffffu, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1).x;
       }
-      for (int o = G >> 1; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFull, n2, o);
-      const uint4 w = philox4x32_10(0xffffffffu, 0x50524F50u, (unsigned)rid, (unsigned)(rid >> 32), k0, k1);
       const float nrm = sqrt_approx(n2);
       const float safe = nrm > 1e-12f ? nrm : 1.0f;
-      f = scale * ex2_approx(lg2_approx(u01_from_bits(w.x)) / (float)d) * rcp_approx(safe);
+      f = scale * ex2_approx(lg2_approx(u01_from_bits(uw)) / (float)d) * rcp_approx(safe);
     }
     for (int b = sub; b < n_blk; b += G) {
       float v[4];

@@ -614,6 +614,22 @@ def test_proposal_plugin_samplers_moments():
         _lib.check(lib.rwmpt_proposal_sample(fam, 20, 0.7, _lib.ptr(ds), 1000, 99, 5, a.data_ptr(), _lib.stream_ptr(dev)))
         _lib.check(lib.rwmpt_proposal_sample(fam, 20, 0.7, _lib.ptr(ds), 1000, 99, 5, b.data_ptr() + 4, _lib.stream_ptr(dev)))
         assert torch.equal(a[:20000], b[1:20001])
+    # the ball sampler row by row: direction = the Normal sampler's row with the same key and row ids (same block counters),
+    # normalised; radius = scale * u^(1/d), u from word 0 of the row's radius call, Philox counter (0xffffffff, 'PROP', row id) --
+    # recomputed on the host.  d = 20 / 10 draw that word on an idle lane of the row's group in the lane's only Philox call (5 blocks on 8
+    # lanes, 3 on 4), d = 32 / 7 / 200 (no idle lane) in a call of its own.
+    from tests._util import philox4x32_10_py
+    seed, base, m = (0x1234 << 32) | 0x9e3779b9, 7_000_000_001, 257
+    for d2 in (20, 10, 32, 7, 200):
+        ball = torch.empty(m * d2, device=dev)
+        nrm = torch.empty(m * d2, device=dev)
+        _lib.check(lib.rwmpt_proposal_sample(2, d2, 1.3, None, m, seed, base, ball.data_ptr(), _lib.stream_ptr(dev)))
+        _lib.check(lib.rwmpt_proposal_sample(0, d2, 1.0, None, m, seed, base, nrm.data_ptr(), _lib.stream_ptr(dev)))
+        ball, nrm = ball.view(m, d2).double().cpu().numpy(), nrm.view(m, d2).double().cpu().numpy()
+        u = np.asarray([(philox4x32_10_py([0xffffffff, 0x50524F50, (base + r) & 0xffffffff, (base + r) >> 32],
+                                          [seed & 0xffffffff, seed >> 32])[0] >> 8) / 16777216.0 for r in range(m)])
+        want = nrm / np.linalg.norm(nrm, axis=1, keepdims=True) * (1.3 * u ** (1.0 / d2))[:, None]
+        np.testing.assert_allclose(ball, want, rtol=2e-4, atol=2e-6, err_msg=f"ball sampler d={d2}")
 
 
 @pytest.mark.parametrize("swap_mode", ["reference", "exchange"])
