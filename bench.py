@@ -104,8 +104,10 @@ def job_gpu_indices(world):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons of the JOB's GPUs, sampled every 200 ms while the timed region runs.  The poller is
-    started during the last warm-up step (its start-up -- NVML initialisation -- stalled the first timed launch by ~25 ms when
-    it was started at the timed region's edge); `mark()` at the start of the timed region drops the rows read before it."""
+    started BEFORE the warm-up steps and the timed region only begins once its first row has arrived: its start-up (NVML
+    initialisation, up to a second on a fresh box) stalls a running kernel by 25-100 ms, which used to land in the first timed
+    step now and then (step_ms [194.7, 167.5, 167.2, ...]); the steady 200 ms polling does not show.  `mark()` at the start of
+    the timed region drops the rows read before it."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -124,6 +126,11 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_ready(self, wait_s=15.0):
+        t_end = time.perf_counter() + wait_s
+        while self.proc is not None and not self.rows and self.proc.poll() is None and time.perf_counter() < t_end:
+            time.sleep(0.02)                                              # start-up still in progress
 
     def mark(self):
         self.t0 = time.perf_counter()
@@ -662,20 +669,25 @@ def main():
         # one nvidia-smi poller per job (rank 0), restricted to the job's own GPUs: NVML queries take a driver lock that CUDA
         # calls of the same process tree can wait on, and idle GPUs of the box would drag the median down
         sampler = ClockSampler(job_gpu_indices(world) if world > 1 else [job_gpu_indices(local + 1)[local]]) if (with_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()                                               # start-up cost lands in the warm-up steps
         for w in range(warmup):
             if sampler and w == warmup - 1:
-                sampler.start()                                           # start-up cost lands in the last warm-up step
+                # the poller's first row must have arrived before the LAST warm-up step: waiting for it leaves the GPU idle (clocks
+                # drop), and the last warm-up step brings it back to speed right before the timed region
+                torch.cuda.synchronize()
+                sampler.wait_ready()
             batch.rewind_storage()
             batch.run(T)
             if world > 1:                                                 # also warms the NCCL communicator up
                 D.allreduce_statistics_tensor(D.local_statistics_tensor(algo))
         torch.cuda.synchronize()
+        if sampler:
+            sampler.wait_ready()                                          # (--warmup 0)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         if sampler:
-            if sampler.proc is None:
-                sampler.start()                                           # --warmup 0
             sampler.mark()                                                # rows from here on belong to the timed region
         evs = []
         launches = 0
