@@ -316,12 +316,16 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
     const size_t swap_floats = (g.smem / sizeof(float) + 3) & ~(size_t)3;
     const char* eb = getenv("RWMPT_BULK_STORE");
     const int bufs = (!ieee && !(eb && atoi(eb) == 0)) ? 2 : 1;
+    // every family but RoughCarpet stages rows with unmasked stores (mcmc_unit, kFastStage): up to E - 1 padding zeros spill past
+    // a buffer's last row, into a slack of 28 floats (E <= 25)
+    const size_t slack = r->target.family == RWMPT_T_ROUGH_CARPET ? 0 : 28;
     int S = 16;
-    while (S > 1 && (size_t)bufs * g.chains_per_cta * (((size_t)S * d + 3) & ~(size_t)3) * sizeof(float) > 32 * 1024) S >>= 1;
-    const size_t st_stride = ((size_t)S * d + 3) & ~(size_t)3;
+    while (S > 1 && (size_t)bufs * g.chains_per_cta * (((size_t)S * d + slack + 3) & ~(size_t)3) * sizeof(float) > 32 * 1024) S >>= 1;
+    const size_t st_stride = ((size_t)S * d + slack + 3) & ~(size_t)3;
     const size_t lp_floats = ((size_t)g.chains_per_cta * S + 1) & ~(size_t)1;
     a.stage_rows = S;
     a.stage_bufs = bufs;
+    a.stage_stride = (int)st_stride;
     a.stage_off = (int)swap_floats;
     const uintptr_t p = reinterpret_cast<uintptr_t>(r->samples);
     a.stage_vw = (d % 4 == 0 && p % 16 == 0) ? 4 : ((d % 2 == 0 && p % 8 == 0) ? 2 : 1);

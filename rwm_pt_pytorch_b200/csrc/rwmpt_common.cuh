@@ -53,6 +53,7 @@ struct KernelArgs {
   int stage_off;   // offset (floats) of the staging region in dynamic shared memory
   int stage_vw;    // floats per vector store of the flush (4, 2 or 1)
   int stage_bufs;  // 2: double-buffered staging, blocks leave through the bulk-copy engine (cp.async.bulk shared -> global)
+  int stage_stride;  // floats between two staging buffers: stage_rows * dim plus the slack the unmasked row stores spill into
   // balanced (time-sliced, ticketed) launch -- see mcmc_kernel; n_slices <= 1: plain launch, CTA b runs unit b
   int n_slices;
   int n_units;            // CTAs of the plain launch (= units of work)

@@ -395,7 +395,6 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   // S*d-float blocks (layout (chain, row, dim): the S rows of one chain are adjacent in HBM) with vector stores of
   // a.stage_vw floats (float4 when d % 4 == 0, float2 when d is even): one warp instruction writes 512 contiguous bytes.
   const int S = a.stage_rows;
-  const int st_stride = (S * d + 3) & ~3;
   // a.stage_bufs == 2: two staging buffers per chain; a full block leaves through the bulk-copy engine (one lane issues
   // cp.async.bulk shared -> global for the chain's S*d*4 contiguous bytes) while the chain stages the next block in the other
   // buffer -- no LDS / STG per lane, no scoreboard wait on the flush.  The engine needs 16-byte aligned source, destination
@@ -410,6 +409,14 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
 #else
   constexpr bool kBulkOk = !(std::is_same<Target<E, IEEE>, RoughCarpetT<E, IEEE, true>>::value || std::is_same<Target<E, IEEE>, RoughCarpetT<E, IEEE, false>>::value);
 #endif
+  // Staging a row costs one STS per coordinate and little else on every family but RoughCarpet (kFastStage): the lane keeps a
+  // pointer to its slot of the current row and stores all E values UNMASKED -- padding coordinates carry exact zeros, and on a
+  // padded mapping (d = 50 on 7 x 8) they land in the head of the NEXT row, which the same warp rewrites one step later, or,
+  // after the block's last row, in the slack the host leaves behind every buffer (a.stage_stride).  The masked form below spent
+  // ~45 instructions per stored step on index arithmetic and predicates (BASELINE config 4: 594 instructions per pair of
+  // steps against ~500 without the stores).
+  constexpr bool kFastStage = kBulkOk;
+  const int st_stride = kFastStage ? a.stage_stride : ((S * d + 3) & ~3);
   const bool bulk = STORE && kBulkOk && a.stage_bufs == 2;
   const int nb = bulk ? 2 : 1;
   float* st_base = smem + a.stage_off;                                        // [chains_per_cta][nb][st_stride]
@@ -418,6 +425,14 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   float* st_x = st_x0;
   int st_buf = 0;
   const bool stage_me = storing && valid;
+  // kFastStage: a lane that stores nothing (all padding, a hot chain when only cold chains are retained, a thread without a
+  // chain) writes into the slack behind its chain's first buffer instead of branching around the stores -- the slack is
+  // never read (S*d + E + 1 <= stage_stride)
+  const bool stage_lane = stage_me && c.base < d;
+  float* const st_dummy = st_x0 + S * d;
+  float* st_row = st_x + c.base;                          // this lane's slot of the row being staged
+  float* const st_lp0 = st_lp_base + (size_t)(in_cta ? cl : 0) * S;
+  float* st_lp_row = st_lp0;                              // the chain's log-density slot of that row
   const bool store_each = has_samples && a.thin == 1 && s_first > a.store_start;  // every step of this run is retained
   int nbuf = 0;
   long long m_base = store_m;   // row index of staged row 0
@@ -470,13 +485,25 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
     m_base += nbuf;
     nbuf = 0;
     flush_at = S;
+    st_row = st_x + c.base;
+    st_lp_row = st_lp0;
   };
   auto stage_row = [&](const float (&xs)[E], float lpv) {
-    if (stage_me) {
+    if constexpr (kFastStage) {
+      float* const pr = stage_lane ? st_row : st_dummy;
 #pragma unroll
-      for (int e = 0; e < E; ++e)
-        if (c.ok(e)) st_x[nbuf * d + c.base + e] = xs[e];
-      if (c.sub == 0) st_lp_base[(size_t)cl * S + nbuf] = lpv;
+      for (int e = 0; e < E; ++e) pr[e] = xs[e];
+      float* const pl = (stage_lane && c.sub == 0) ? st_lp_row : st_dummy + E;
+      *pl = lpv;
+      st_row += d;
+      ++st_lp_row;
+    } else {
+      if (stage_me) {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if (c.ok(e)) st_x[nbuf * d + c.base + e] = xs[e];
+        if (c.sub == 0) st_lp_base[(size_t)cl * S + nbuf] = lpv;
+      }
     }
     ++nbuf;
     if (nbuf == flush_at) stage_flush();
