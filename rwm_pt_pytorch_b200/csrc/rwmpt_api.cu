@@ -319,8 +319,18 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
     // every family but RoughCarpet stages rows with unmasked stores (mcmc_unit, kFastStage): up to E - 1 padding zeros spill past
     // a buffer's last row, into a slack of 28 floats (E <= 25)
     const size_t slack = r->target.family == RWMPT_T_ROUGH_CARPET ? 0 : 28;
+    // Staging budget per CTA: 32 KiB, or up to 64 KiB when the launch has so few CTAs per SM that all of them stay resident with
+    // the larger blocks (BASELINE config 4: 512 CTAs on 148 SMs, 16 rows instead of 8 per flush: 7.35e9 -> 7.83e9 chain-steps/s;
+    // 4 rows: 6.63e9).  RWMPT_STAGE_KIB overrides for A/B measurements.
+    const long long ctas_per_sm = (g.grid + (g.sms > 0 ? g.sms : 148) - 1) / (g.sms > 0 ? g.sms : 148);
+    const size_t per_cta = (size_t)227 * 1024 / (size_t)(ctas_per_sm < 1 ? 1 : (ctas_per_sm > 32 ? 32 : ctas_per_sm)) - 1024;
+    const size_t fixed = swap_floats * sizeof(float) + (size_t)g.chains_per_cta * 16 * sizeof(float) + 64;
+    size_t stage_cap = per_cta > fixed + 32 * 1024 ? per_cta - fixed : 32 * 1024;
+    if (stage_cap > 64 * 1024) stage_cap = 64 * 1024;
+    const char* ek = getenv("RWMPT_STAGE_KIB");
+    if (ek && atoi(ek) >= 4 && atoi(ek) <= 160) stage_cap = (size_t)atoi(ek) * 1024;
     int S = 16;
-    while (S > 1 && (size_t)bufs * g.chains_per_cta * (((size_t)S * d + slack + 3) & ~(size_t)3) * sizeof(float) > 32 * 1024) S >>= 1;
+    while (S > 1 && (size_t)bufs * g.chains_per_cta * (((size_t)S * d + slack + 3) & ~(size_t)3) * sizeof(float) > stage_cap) S >>= 1;
     const size_t st_stride = ((size_t)S * d + slack + 3) & ~(size_t)3;
     const size_t lp_floats = ((size_t)g.chains_per_cta * S + 1) & ~(size_t)1;
     a.stage_rows = S;
