@@ -318,28 +318,38 @@ static int run_impl(const rwmpt_run_args_t* r, void* stream, bool require_rwm) {
     const int bufs = (!ieee && !(eb && atoi(eb) == 0)) ? 2 : 1;
     // every family but RoughCarpet stages rows with unmasked stores (mcmc_unit, kFastStage): up to E - 1 padding zeros spill past
     // a buffer's last row, into a slack of 28 floats (E <= 25)
-    const size_t slack = r->target.family == RWMPT_T_ROUGH_CARPET ? 0 : 28;
+    // ... and the buffers hold one row more than a block (the fast loop tests for a full block once per pair of steps)
+    const bool fast_stage = r->target.family != RWMPT_T_ROUGH_CARPET;
+    const size_t slack = fast_stage ? (size_t)d + 28 : 0;
     // Staging budget per CTA: 32 KiB, or up to 64 KiB when the launch has so few CTAs per SM that all of them stay resident with
     // the larger blocks (BASELINE config 4: 512 CTAs on 148 SMs, 16 rows instead of 8 per flush: 7.35e9 -> 7.83e9 chain-steps/s;
     // 4 rows: 6.63e9).  RWMPT_STAGE_KIB overrides for A/B measurements.
     const long long ctas_per_sm = (g.grid + (g.sms > 0 ? g.sms : 148) - 1) / (g.sms > 0 ? g.sms : 148);
     const size_t per_cta = (size_t)227 * 1024 / (size_t)(ctas_per_sm < 1 ? 1 : (ctas_per_sm > 32 ? 32 : ctas_per_sm)) - 1024;
-    const size_t fixed = swap_floats * sizeof(float) + (size_t)g.chains_per_cta * 16 * sizeof(float) + 64;
+    const size_t fixed = swap_floats * sizeof(float) + (size_t)g.chains_per_cta * 17 * sizeof(float) + 64;
     size_t stage_cap = per_cta > fixed + 32 * 1024 ? per_cta - fixed : 32 * 1024;
     if (stage_cap > 64 * 1024) stage_cap = 64 * 1024;
     const char* ek = getenv("RWMPT_STAGE_KIB");
     if (ek && atoi(ek) >= 4 && atoi(ek) <= 160) stage_cap = (size_t)atoi(ek) * 1024;
+    int bufs_eff = bufs;
+    auto stage_bytes = [&](int rows) { return (size_t)bufs_eff * g.chains_per_cta * (((size_t)rows * d + slack + 3) & ~(size_t)3) * sizeof(float); };
     int S = 16;
-    while (S > 1 && (size_t)bufs * g.chains_per_cta * (((size_t)S * d + slack + 3) & ~(size_t)3) * sizeof(float) > stage_cap) S >>= 1;
+    if (fast_stage) {
+      // an even number of rows, at least two: blocks then end where the next one starts 16-byte aligned whenever d is even
+      while (S > 2 && stage_bytes(S) > stage_cap) S -= 2;
+      if (stage_bytes(S) > 160 * 1024) bufs_eff = 1;   // a very wide CTA: single buffer, vector flush
+    } else {
+      while (S > 1 && stage_bytes(S) > stage_cap) S >>= 1;
+    }
     const size_t st_stride = ((size_t)S * d + slack + 3) & ~(size_t)3;
-    const size_t lp_floats = ((size_t)g.chains_per_cta * S + 1) & ~(size_t)1;
+    const size_t lp_floats = ((size_t)g.chains_per_cta * (S + 1) + 1) & ~(size_t)1;
     a.stage_rows = S;
-    a.stage_bufs = bufs;
+    a.stage_bufs = bufs_eff;
     a.stage_stride = (int)st_stride;
     a.stage_off = (int)swap_floats;
     const uintptr_t p = reinterpret_cast<uintptr_t>(r->samples);
     a.stage_vw = (d % 4 == 0 && p % 16 == 0) ? 4 : ((d % 2 == 0 && p % 8 == 0) ? 2 : 1);
-    g.smem = (swap_floats + (size_t)bufs * g.chains_per_cta * st_stride + lp_floats) * sizeof(float);
+    g.smem = (swap_floats + (size_t)bufs_eff * g.chains_per_cta * st_stride + lp_floats) * sizeof(float);
   }
   // Few warps per GPU (strong scaling of config 3, config 2's 4096 chains): the warp-specialised kernel (rwmpt_spec.cuh) takes the
   // regular middle of the run, mcmc_kernel the edges -- up to the first even step at or past burn-in, and an odd last step --

@@ -427,11 +427,11 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
   const bool stage_me = storing && valid;
   // kFastStage: a lane that stores nothing (all padding, a hot chain when only cold chains are retained, a thread without a
   // chain) writes into the slack behind its chain's first buffer instead of branching around the stores -- the slack is
-  // never read (S*d + E + 1 <= stage_stride)
+  // never read ((S + 1)*d + E + 1 <= stage_stride: S rows of a block, the overshoot row of stage_put, the slack)
   const bool stage_lane = stage_me && c.base < d;
-  float* const st_dummy = st_x0 + S * d;
+  float* const st_dummy = st_x0 + (S + 1) * d;
   float* st_row = st_x + c.base;                          // this lane's slot of the row being staged
-  float* const st_lp0 = st_lp_base + (size_t)(in_cta ? cl : 0) * S;
+  float* const st_lp0 = st_lp_base + (size_t)(in_cta ? cl : 0) * (S + 1);   // kFastStage: S + 1 slots per chain (see stage_put)
   float* st_lp_row = st_lp0;                              // the chain's log-density slot of that row
   const bool store_each = has_samples && a.thin == 1 && s_first > a.store_start;  // every step of this run is retained
   int nbuf = 0;
@@ -473,7 +473,7 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
         for (int v = c.sub; v < n; v += W) dst[v] = src[v];
       }
       if (a.sample_logp != nullptr)
-        for (int r = c.sub; r < (int)rows; r += W) a.sample_logp[store_chain * a.sample_stride + m_base + r] = st_lp_base[(size_t)cl * S + r];
+        for (int r = c.sub; r < (int)rows; r += W) a.sample_logp[store_chain * a.sample_stride + m_base + r] = kFastStage ? st_lp0[r] : st_lp_base[(size_t)cl * S + r];
     }
     if (bulk) {
       // switch buffers; the block that left from the other buffer one flush ago must have been read completely
@@ -506,7 +506,29 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
       }
     }
     ++nbuf;
-    if (nbuf == flush_at) stage_flush();
+    if (kFastStage ? nbuf >= flush_at : nbuf == flush_at) stage_flush();
+  };
+  // kFastStage, fast loop: the two rows of a pair of steps are staged WITHOUT a flush test in between, so that the pair stays one
+  // basic block; the test comes once, after the second row.  A block boundary inside the pair (d = 50: blocks start on even
+  // rows, pairs on odd ones) overshoots by one row -- the buffers hold S + 1 rows -- and that row, which is the current
+  // state, is staged again as the first row of the next block.
+  auto stage_put = [&](const float (&xs)[E], float lpv) {
+    float* const pr = stage_lane ? st_row : st_dummy;
+#pragma unroll
+    for (int e = 0; e < E; ++e) pr[e] = xs[e];
+    float* const pl = (stage_lane && c.sub == 0) ? st_lp_row : st_dummy + E;
+    *pl = lpv;
+    st_row += d;
+    ++st_lp_row;
+    ++nbuf;
+  };
+  auto stage_pair_end = [&](const float (&xs)[E], float lpv) {
+    if (nbuf >= flush_at) {
+      const bool over = nbuf > flush_at;   // warp-uniform, like nbuf and flush_at
+      nbuf = flush_at;
+      stage_flush();
+      if (over) stage_put(xs, lpv);
+    }
   };
   const long long burn_t = a.burn_in > step_offset ? a.burn_in - step_offset : 0;  // local steps t >= burn_t count
 
@@ -730,7 +752,10 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
     jf += jadd;
     lp = acc ? lpp : lp;
     cnt += acc ? 1u : 0u;
-    if constexpr (decltype(store_tag)::value) stage_row(x, lp);
+    if constexpr (decltype(store_tag)::value) {
+      if constexpr (kFastStage) stage_put(x, lp);
+      else stage_row(x, lp);
+    }
   };
 
   const bool inject = TEST && a.inj_inc != nullptr;
@@ -878,7 +903,14 @@ __device__ __forceinline__ void mcmc_unit(const KernelArgs& a, const long long c
               plo_end = plo + (uint32_t)len;
             }
           }
-          if constexpr (decltype(store_tag)::value) stage_row(x, lp);  // retained after the sweep, like the reference
+          if constexpr (decltype(store_tag)::value) {  // retained after the sweep, like the reference
+            if constexpr (kFastStage) {
+              stage_put(x, lp);
+              stage_pair_end(x, lp);
+            } else {
+              stage_row(x, lp);
+            }
+          }
           if (done) break;
         }
         n_done = n_here;
